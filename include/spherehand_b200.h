@@ -1,0 +1,165 @@
+/* spherehand_b200 — C ABI of the B200 (sm_100a) hot path of melonwan/sphereHand.
+ *
+ * libspherehand_b200.so exports exactly the functions declared here.  All of them:
+ *   - take plain device pointers and sizes (no torch types), never allocate device memory, never synchronise;
+ *   - launch on the CUDA stream passed last (a `cudaStream_t` cast to `void*`; NULL = legacy default stream, which is
+ *     what the reference kernel uses, depth_rasterization_cuda_kernel.cu:125);
+ *   - return 0 on success, 1 = invalid argument, 2 = CUDA error, 3 = unsupported shape; `sh_last_error()` holds the text;
+ *   - borrow their inputs (never mutated) and write only the buffers documented as outputs, which the caller owns.
+ * Tensors are contiguous, fp32 unless stated; "bf16" is __nv_bfloat16.  file:line citations are into the reference
+ * tree (melonwan/sphereHand @ 4a5bae9) and name the interface each entry replaces.
+ *
+ * The reference's only FFI is the pybind function `depth_rasterization.forward(width, height, vertices)`
+ * (mesh/cuda_kernel/depth_rasterization_cuda.cpp:15-25); `sh_tri_raster_fwd` is its drop-in.  Every other entry
+ * is what a native binding for the corresponding Python module of the hot path would bind.
+ */
+#ifndef SPHEREHAND_B200_H
+#define SPHEREHAND_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------ library */
+int sh_abi_version(void);
+const char* sh_build_arch(void);      /* "sm_100a" */
+const char* sh_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------ R1: triangle rasteriser
+ * Replaces depth_rasterization_cuda_forward + kernel, mesh/cuda_kernel/depth_rasterization_cuda_kernel.cu:18-134.
+ * face_vertices [B,F,3,3]; out [B,H,W], written with 1000.0 where nothing is drawn. */
+int sh_tri_raster_fwd(const void* face_vertices, int B, int F, int W, int H, void* out, void* stream);
+/* Same rasteriser evaluated only at the pixels {c*step + off0 + o, o < noff}^2 of the virtual W x H image, compact
+ * output [B,oh,ow] (oh = H/step*noff): exactly the samples DepthRasterization.forward's bilinear resize reads
+ * (mesh/render.py:310-311; step 5/off 2/noff 1 for 640->128, step 10/off 4/noff 2 for 640->64). */
+int sh_tri_raster_lattice_fwd(const void* face_vertices, int B, int F, int W, int H, int step, int off0, int noff,
+                              void* out, int oh, int ow, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ R2: sphere renderer
+ * Replaces BallRender.forward (mesh/render.py:26-53) + min over spheres (mesh/render.py:89,
+ * mesh/multiview_utility.py:76) and their autograd backward.
+ * spheres float4 [N*J] = (cx,cy,cz,r), 16-byte aligned; depth [N,H,W]; idx uint8 [N,H,W] (255 = background);
+ * grad_spheres float4 [N*J] = dL/d(cx,cy,cz,r) (overwritten).  1 <= J <= 64. */
+int sh_sphere_render_fwd(const void* spheres, int N, int J, int H, int W, void* depth, void* idx, void* stream);
+int sh_sphere_render_bwd(const void* grad_depth, const void* idx, const void* spheres, int N, int J, int H, int W,
+                         void* grad_spheres, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ fused MutualProjectionLoss
+ * Replaces MutualProjectionLoss.forward (mesh/multiview_utility.py:90-130) incl. MutualTransformation (:13-30),
+ * MutualProjection (:55-77), DataToModelLoss (mesh/render.py:123-142) and the backward to `joints`.
+ * cam, inv_cam [B,V,4,4]; joints [B,V,J,3]; real [B,V,H,W]; radii [J];
+ * out: projected_dms [B,V,V,H,W]; loss3 = (loss, model_to_data, data_to_model); grad_joints [B,V,J,3] = dloss/djoints.
+ * scratch: sh_mvproj_scratch_bytes(B,V,J) bytes, 16-byte aligned.  V <= 8, B*V*V <= 65535. */
+size_t sh_mvproj_scratch_bytes(int B, int V, int J);
+int sh_mvproj_loss_fwdbwd(const void* cam, const void* inv_cam, const void* joints, const void* real, const void* radii,
+                          int B, int V, int J, int H, int W, int is_mv, void* projected_dms, void* loss3,
+                          void* grad_joints, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ small pose-space heads
+ * Replaces MultiviewConsistencyLoss.forward (mesh/multiview_utility.py:138-167, hm_weight=None), CollisionLoss.forward
+ * (mesh/render.py:168-176) and BoneLengthLoss.forward (mesh/render.py:196-206) with their backward.
+ * flags: bit0 consistency, bit1 collision, bit2 bone length (the latter two need J == 41 and only see view 0, as the
+ * reference does).  losses3 = (consistency, collision, bone_length); grads3 [3,B,V,J,3]; scratch >= 32 bytes. */
+int sh_pose_losses_fwdbwd(const void* cam, const void* joints, int B, int V, int J, int flags, float min_dist,
+                          void* losses3, void* grads3, void* scratch, void* stream);
+
+/* Replaces PoseVae.prior_loss (network/pose_vae.py:81-89).  x [M,123] (= xyz/100), eps [M,32] ~ N(0,1) drawn by the
+ * host, weight_blob: sh_vae_blob_floats() floats packed as documented in csrc/pose_vae.cu.
+ * loss3 = (loss, recon_mse, kld); grad_x [M,123]; scratch >= 16 bytes, 8-byte aligned. */
+size_t sh_vae_blob_floats(void);
+int sh_vae_prior_fwdbwd(const void* x, const void* eps, const void* weight_blob, int M, void* loss3, void* grad_x,
+                        void* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ heat-map heads
+ * Replaces RecoverXYZCoordinateFromHeatmap.forward (network/util_modules.py:182-201), the uv/d channel split of
+ * HeatmapEstimationNetwork.forward (network/create_network_and_criterion.py:111-123) and the heat-map MSE terms of
+ * MultiTaskLoss.forward (:188-193, :231-235).  score [N,C,h,w] NCHW (uv = channels [0,J), depth = [J,2J));
+ * samples n < Ns are synthetic (MSE against target_uv [Ns,J,h,w]), the rest real (MSE against 0).
+ * fwd: xyz [N,J,3] mm; sse2 double[2] = (sum (uv-target)^2, sum uv_real^2) or NULL.
+ * bwd: gscore [N,C,h,w] = d/dscore of (xyz . gxyz) + c_synt/2*sse_synt + c_real/2*sse_real  (overwrites 2J channels). */
+int sh_softargmax_fwd(const void* score, int N, int Ns, int J, int C, int h, int w, float depth_scale_inv,
+                      const void* target_uv, void* xyz, void* sse2, void* stream);
+int sh_softargmax_bwd(const void* score, const void* gxyz, int N, int Ns, int J, int C, int h, int w,
+                      float depth_scale_inv, const void* target_uv, float c_synt, float c_real, void* gscore,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------ synthetic branch
+ * sh_fk_fwd replaces HandTransformationMat.forward (mesh/kinematicsTransformation.py:169-177) and, when `scales`
+ * [B,3] is given, RandScale.forward (mesh/pointTransformation.py:135-148).  params [B,26]; offset_mats,
+ * inv_offset_mats [17,4,4]; mats [B,17,4,4]. */
+int sh_fk_fwd(const void* params, const void* scales, const void* offset_mats, const void* inv_offset_mats, int B,
+              void* mats, void* stream);
+/* LinearBlendSkinning.forward (mesh/pointTransformation.py:39-46) over a CSR of the non-zero weights, optionally fused
+ * with OthographicalProjection.forward (:84-99): mode 0 none, 1 per-sample focal jitter rand_f [B], 2 K-matrix.
+ * row_ptr int32 [Nv+1], bone int32 [nnz], wv float4 [nnz]; out_points float4 [B,Nv]. */
+int sh_lbs_fwd(const void* mats, const void* row_ptr, const void* bone, const void* wv, int B, int Nv, int right_hand,
+               int mode, float cx, float cy, float fx, float fy, const void* rand_f, void* out_points, void* stream);
+/* face_vertices[b,f,3,3] = points[b, faces[f,:], 0:3]   (mesh/render.py:308-309); faces int32 [F,3]. */
+int sh_gather_faces(const void* points, const void* faces, int B, int Nv, int F, void* face_vertices, void* stream);
+/* clamp(max=100) + bilinear resize + * depth_scale on the lattice z-buffer (mesh/render.py:286,311;
+ * network/util_modules.py:112): z [B,S*noff,S*noff] -> dm [B,S,S]. */
+int sh_lattice_to_depth(const void* z, int B, int S, int noff, float depth_scale, void* dm, void* stream);
+/* DepthNoise.forward (network/util_modules.py:60-84) with the three N(0,1) draws supplied by the caller. */
+int sh_depth_noise(const void* dm, const void* nx, const void* ny, const void* nz, int B, int H, int W, float sx,
+                   float sy, float sz, void* out, void* stream);
+/* HeatmapRender.forward + InverseOthographicalProjection (mesh/render.py:226-248, 274-279): uvd float4 [B,J] ->
+ * uv_hms, d_hms [B,J,hm,hm], xyz float4 [B,J]. */
+int sh_heatmap_render(const void* uvd, int B, int J, int hm, float sigma, float uv_scale, float depth_scale, float cx,
+                      float cy, float fx, float fy, void* uv_hms, void* d_hms, void* xyz, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ hourglass layers
+ * Activations are NHWC bf16.  `stats` buffers are fp32 [N,G,2] (sum, sum of squares per sample and GroupNorm group),
+ * accumulated atomically: zero them before the producing call.  Replaces nn.Conv2d / nn.GroupNorm / ReLU /
+ * F.max_pool2d / F.interpolate of network/hourglass.py:7-41, 44-85, 88-173.
+ *
+ * sh_conv_fwd: stride-1 'same' convolution as an implicit GEMM on tcgen05 tensor cores.
+ *   x bf16 [N,H,W,Cin] (Cin % 64 == 0; H, W powers of two >= 4); w bf16 [taps, cout_pad, Cin] (taps = 1 or 9, tap-major,
+ *   rows >= Cout zero); bias fp32 [Cout] or NULL; residual bf16 [N,H,W,Cout] or NULL;
+ *   y bf16 [N,H,W,y_ld] or NULL; y_nchw fp32 [N,Cout,H,W] or NULL; stats of the (rounded) output or NULL.
+ *   The data gradient is the same call on dY with the flipped/transposed weights produced by sh_pack_weights. */
+int sh_conv_fwd(const void* x, const void* w, const void* bias, const void* residual, int N, int H, int W, int Cin,
+                int Cout, int cout_pad, int taps, void* y, int y_ld, void* y_nchw, void* stats, int groups,
+                void* stream);
+/* dw fp32 [Cout,Cin,k,k] (reference layout) += dY^T X (accumulated atomically: zero first).  dy bf16 [N,H,W,dy_C],
+ * x bf16 [N,H,W,x_C]; x_C, dy_C multiples of 64; Cin <= x_C and Cout <= dy_C are the real channel counts. */
+int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout, int taps,
+                  void* dw, void* stream);
+/* GroupNorm(G) + ReLU: y = relu(gn(x)); optional statistics of y for a following GroupNorm(G_out). */
+int sh_gn_relu_fwd(const void* x, const void* stats_in, const void* gamma, const void* beta, int N, int HW, int C,
+                   int G, float eps, void* y, void* stats_out, int G_out, void* stream);
+/* Backward of the above: dx = d/dx (+ addend), dgamma/dbeta accumulated, optional column sum of dx (bias gradient of
+ * the convolution that produced x).  red: scratch fp32 [N,G,2]. */
+int sh_gn_relu_bwd(const void* da, const void* x, const void* stats_in, const void* gamma, const void* beta,
+                   const void* addend, int N, int HW, int C, int G, float eps, void* red, void* dgamma, void* dbeta,
+                   void* dx, void* colsum, void* stream);
+int sh_maxpool_fwd(const void* x, int N, int H, int W, int C, void* y, void* stats_out, int G_out, void* stream);
+int sh_maxpool_bwd(const void* dy, const void* x, const void* addend, int N, int H, int W, int C, void* dx,
+                   void* colsum, void* stream);
+int sh_upsample_add_fwd(const void* up1, const void* low, int N, int h, int w, int C, void* y, void* stats_out,
+                        int G_out, void* stream);
+int sh_upsample_bwd(const void* dy, int N, int h, int w, int C, void* dlow, void* colsum, void* stream);
+int sh_add(const void* a, const void* b, const void* c, int N, int HW, int C, void* y, void* stats_out, int G_out,
+           void* colsum, void* stream);
+int sh_colsum(const void* x, int N, int HW, int C, void* colsum, void* stream);
+/* Stem: 5x5 stride-2 convolution 1 -> 64 channels (network/hourglass.py:95-96).  img fp32 [N,S,S]; w fp32 [64,1,5,5]. */
+int sh_stem_conv_fwd(const void* img, const void* w, const void* b, int N, int S, void* y, void* stats_out, int G_out,
+                     void* stream);
+int sh_stem_conv_wgrad(const void* img, const void* dy, int N, int S, void* dw, void* db, void* stream);
+/* Layout conversion between the reference's fp32 NCHW tensors and the internal bf16 NHWC (channels padded to Cp). */
+int sh_nchw_to_nhwc(const void* x, int N, int C, int HW, int Cp, void* y, void* stream);
+int sh_nhwc_to_nchw(const void* x, int N, int C, int HW, void* y, void* stream);
+/* fp32 master weight [Cout,Cin,k,k] -> bf16 forward layout wf [taps,cout_pad,cin_pad] and (optional) data-gradient
+ * layout wb [taps,b_rows,b_cols] (flipped taps, transposed). */
+int sh_pack_weights(const void* w, int Cout, int Cin, int taps, int cout_pad, int cin_pad, int b_rows, int b_cols,
+                    void* wf, void* wb, void* stream);
+int sh_unpack_wgrad(const void* dw, int Cout, int Cin, int taps, int cout_ld, int cin_ld, void* grad, void* stream);
+/* torch.optim.Adam step with L2 weight decay on flat fp32 buffers (network/engine.py:95-97); grad is read as g*grad_scale. */
+int sh_adam_step(void* p, const void* g, void* m, void* v, long n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHEREHAND_B200_H */

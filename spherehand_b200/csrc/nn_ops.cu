@@ -1,0 +1,860 @@
+// Memory-bound layers of the hourglass (sm_100a): GroupNorm(+ReLU) forward/backward, 2x2 max-pool, bilinear x2
+// up-sampling fused with the skip add, the 5x5 stride-2 stem convolution (Cin = 1), layout conversions, weight
+// re-packing and the flat Adam step.
+//
+// Replaces the ATen kernels behind
+//   nn.GroupNorm + ReLU(inplace)        /root/reference/network/hourglass.py:26-36, 97, 139-145, 153-155
+//   F.max_pool2d(2, 2)                  /root/reference/network/hourglass.py:70, 158
+//   F.interpolate(x2, bilinear) + add   /root/reference/network/hourglass.py:79-81
+//   conv1 (5x5, stride 2, 1 -> 64)      /root/reference/network/hourglass.py:95-96, 153
+//   torch.optim.Adam(lr, wd=1e-5)       /root/reference/network/engine.py:95-97
+// All activations are NHWC bf16; every kernel that produces a tensor consumed by a GroupNorm also accumulates that
+// tensor's per-(sample, group) sum / sum-of-squares (fp32 atomics into stats[N,G,2]) so normalisation never needs
+// a separate reduction pass; kernels that produce an output-gradient tensor optionally accumulate its per-channel
+// column sum (the bias gradient of the producing convolution).  These kernels are HBM-bound: 16-byte vector
+// accesses (8 bf16 channels per thread), grid = (chunks, N) with >= 2 waves of 148 SMs.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kT = 256;
+
+struct bf8 { float v[8]; };
+
+__device__ __forceinline__ bf8 load8(const __nv_bfloat16* p) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t r[4] = {u.x, u.y, u.z, u.w};
+    bf8 o;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        o.v[2 * e] = __uint_as_float(r[e] << 16);
+        o.v[2 * e + 1] = __uint_as_float(r[e] & 0xffff0000u);
+    }
+    return o;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, bf8& x) {
+    uint32_t r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 b = __floats2bfloat162_rn(x.v[2 * e], x.v[2 * e + 1]);
+        r[e] = *reinterpret_cast<const uint32_t*>(&b);
+        x.v[2 * e] = __uint_as_float(r[e] << 16);              // hand back the rounded values
+        x.v[2 * e + 1] = __uint_as_float(r[e] & 0xffff0000u);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(r[0], r[1], r[2], r[3]);
+}
+
+// Per-thread running sum / sumsq of its 8 channels (the channel vector of a thread never changes, so its group(s)
+// are fixed): st = {s1, s2} for gs >= 8, {s1_lo, s2_lo, s1_hi, s2_hi} for gs == 4.  Flushed once into s_st[G][2].
+__device__ __forceinline__ void stats_accum(float* st, const bf8& x, int gs) {
+    if (gs >= 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { st[0] += x.v[e]; st[1] += x.v[e] * x.v[e]; }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { st[0] += x.v[e]; st[1] += x.v[e] * x.v[e]; st[2] += x.v[4 + e]; st[3] += x.v[4 + e] * x.v[4 + e]; }
+    }
+}
+__device__ __forceinline__ void stats_flush(float* s_st, const float* st, int c0, int gs) {
+    if (gs >= 8) {
+        atomicAdd(&s_st[(c0 / gs) * 2], st[0]);
+        atomicAdd(&s_st[(c0 / gs) * 2 + 1], st[1]);
+    } else {
+        atomicAdd(&s_st[(c0 / 4) * 2], st[0]); atomicAdd(&s_st[(c0 / 4) * 2 + 1], st[1]);
+        atomicAdd(&s_st[(c0 / 4 + 1) * 2], st[2]); atomicAdd(&s_st[(c0 / 4 + 1) * 2 + 1], st[3]);
+    }
+}
+
+// Thread mapping shared by the elementwise NHWC kernels: blockIdx.y = sample n, a block walks pixel rows
+// [blockIdx.x * ppb, ...) of that sample; lane-in-pixel = channel vector.
+struct Walk {
+    int vecs;        // C / 8
+    int rows;        // pixel rows processed concurrently = kT / vecs
+    int cv;          // this thread's channel vector
+    int r;           // this thread's row slot
+};
+__device__ __forceinline__ Walk make_walk(int C) {
+    Walk w;
+    w.vecs = C / 8;
+    w.rows = kT / w.vecs;
+    w.cv = threadIdx.x % w.vecs;
+    w.r = threadIdx.x / w.vecs;
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm + ReLU
+// y = relu((x - mean) * rstd * gamma + beta), statistics from stats_in[N,G,2] over `cnt` = HW*C/G elements.
+__global__ void __launch_bounds__(kT) gn_relu_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats_in,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         int HW, int C, int G, int ppb, float eps, __nv_bfloat16* __restrict__ y,
+                                                         float* __restrict__ stats_out, int G_out) {
+    __shared__ float s_mr[32 * 2];
+    __shared__ float s_st[32 * 2];
+    const int n = blockIdx.y;
+    const int gs = C / G;
+    const float cnt_inv = 1.f / ((float)HW * gs);
+    if (threadIdx.x < G) {
+        const float s1 = stats_in[((size_t)n * G + threadIdx.x) * 2], s2 = stats_in[((size_t)n * G + threadIdx.x) * 2 + 1];
+        const float mean = s1 * cnt_inv;
+        const float var = fmaxf(s2 * cnt_inv - mean * mean, 0.f);
+        s_mr[threadIdx.x * 2] = mean;
+        s_mr[threadIdx.x * 2 + 1] = rsqrtf(var + eps);
+    }
+    if (threadIdx.x < 64) s_st[threadIdx.x] = 0.f;
+    __syncthreads();
+    const Walk w = make_walk(C);
+    const int c0 = w.cv * 8;
+    float ga[8], be[8], mu[8], rs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        ga[e] = gamma[c0 + e]; be[e] = beta[c0 + e];
+        mu[e] = s_mr[((c0 + e) / gs) * 2]; rs[e] = s_mr[((c0 + e) / gs) * 2 + 1];
+    }
+    float st[4] = {0.f, 0.f, 0.f, 0.f};
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
+    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
+        const size_t o = ((size_t)n * HW + pp) * C + c0;
+        bf8 v = load8(x + o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] = fmaxf((v.v[e] - mu[e]) * rs[e] * ga[e] + be[e], 0.f);
+        store8(y + o, v);
+        if (stats_out) stats_accum(st, v, C / G_out);
+    }
+    if (stats_out) {
+        stats_flush(s_st, st, c0, C / G_out);
+        __syncthreads();
+        if (threadIdx.x < G_out * 2) atomicAdd(&stats_out[(size_t)n * G_out * 2 + threadIdx.x], s_st[threadIdx.x]);
+    }
+}
+
+// Backward pass 1: per-(n,g) sums  A = sum dxh, Bq = sum dxh * xhat  (dxh = dy*gamma, dy = da*[y>0]) and per-channel
+// dgamma = sum dy*xhat, dbeta = sum dy.  red[N,G,2] and dgamma/dbeta[C] are accumulated atomically.
+__global__ void __launch_bounds__(kT) gn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ x,
+                                                                const float* __restrict__ stats_in, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, int HW, int C, int G, int ppb,
+                                                                float eps, float* __restrict__ red, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta) {
+    __shared__ float s_mr[32 * 2];
+    __shared__ float s_red[32 * 2];
+    __shared__ float s_gb[2][256];
+    const int n = blockIdx.y;
+    const int gs = C / G;
+    const float cnt_inv = 1.f / ((float)HW * gs);
+    if (threadIdx.x < G) {
+        const float s1 = stats_in[((size_t)n * G + threadIdx.x) * 2], s2 = stats_in[((size_t)n * G + threadIdx.x) * 2 + 1];
+        const float mean = s1 * cnt_inv;
+        const float var = fmaxf(s2 * cnt_inv - mean * mean, 0.f);
+        s_mr[threadIdx.x * 2] = mean;
+        s_mr[threadIdx.x * 2 + 1] = rsqrtf(var + eps);
+    }
+    if (threadIdx.x < 64) s_red[threadIdx.x] = 0.f;
+    for (int i = threadIdx.x; i < 512; i += kT) (&s_gb[0][0])[i] = 0.f;
+    __syncthreads();
+    const Walk w = make_walk(C);
+    const int c0 = w.cv * 8;
+    float ga[8], be[8], mu[8], rs[8], dg[8], db[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        ga[e] = gamma[c0 + e]; be[e] = beta[c0 + e];
+        mu[e] = s_mr[((c0 + e) / gs) * 2]; rs[e] = s_mr[((c0 + e) / gs) * 2 + 1];
+        dg[e] = 0.f; db[e] = 0.f;
+    }
+    float A[2] = {0.f, 0.f}, Bq[2] = {0.f, 0.f};
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
+    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
+        const size_t o = ((size_t)n * HW + pp) * C + c0;
+        const bf8 xv = load8(x + o);
+        const bf8 gv = load8(da + o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float xh = (xv.v[e] - mu[e]) * rs[e];
+            const float dy = (xh * ga[e] + be[e] > 0.f) ? gv.v[e] : 0.f;
+            dg[e] += dy * xh;
+            db[e] += dy;
+            const float dxh = dy * ga[e];
+            const int h = (gs == 4) ? (e >> 2) : 0;
+            A[h] += dxh;
+            Bq[h] += dxh * xh;
+        }
+    }
+    if (gs == 4) {
+        atomicAdd(&s_red[(c0 / 4) * 2], A[0]); atomicAdd(&s_red[(c0 / 4) * 2 + 1], Bq[0]);
+        atomicAdd(&s_red[(c0 / 4 + 1) * 2], A[1]); atomicAdd(&s_red[(c0 / 4 + 1) * 2 + 1], Bq[1]);
+    } else {
+        atomicAdd(&s_red[(c0 / gs) * 2], A[0]); atomicAdd(&s_red[(c0 / gs) * 2 + 1], Bq[0]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { atomicAdd(&s_gb[0][c0 + e], dg[e]); atomicAdd(&s_gb[1][c0 + e], db[e]); }
+    __syncthreads();
+    if (threadIdx.x < G * 2) atomicAdd(&red[(size_t)n * G * 2 + threadIdx.x], s_red[threadIdx.x]);
+    for (int c = threadIdx.x; c < C; c += kT) { atomicAdd(&dgamma[c], s_gb[0][c]); atomicAdd(&dbeta[c], s_gb[1][c]); }
+}
+
+// Backward pass 2: dx = rstd * (dxh - A/m - xhat * Bq/m) (+ addend);  optional column sum of dx into colsum[C].
+__global__ void __launch_bounds__(kT) gn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ x,
+                                                               const float* __restrict__ stats_in, const float* __restrict__ red,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               const __nv_bfloat16* __restrict__ addend, int HW, int C, int G, int ppb,
+                                                               float eps, __nv_bfloat16* __restrict__ dx, float* __restrict__ colsum) {
+    __shared__ float s_mr[32 * 4];
+    __shared__ float s_cs[256];
+    const int n = blockIdx.y;
+    const int gs = C / G;
+    const float cnt_inv = 1.f / ((float)HW * gs);
+    if (threadIdx.x < G) {
+        const float s1 = stats_in[((size_t)n * G + threadIdx.x) * 2], s2 = stats_in[((size_t)n * G + threadIdx.x) * 2 + 1];
+        const float mean = s1 * cnt_inv;
+        const float var = fmaxf(s2 * cnt_inv - mean * mean, 0.f);
+        s_mr[threadIdx.x * 4] = mean;
+        s_mr[threadIdx.x * 4 + 1] = rsqrtf(var + eps);
+        s_mr[threadIdx.x * 4 + 2] = red[((size_t)n * G + threadIdx.x) * 2] * cnt_inv;
+        s_mr[threadIdx.x * 4 + 3] = red[((size_t)n * G + threadIdx.x) * 2 + 1] * cnt_inv;
+    }
+    if (threadIdx.x < 256) s_cs[threadIdx.x] = 0.f;
+    __syncthreads();
+    const Walk w = make_walk(C);
+    const int c0 = w.cv * 8;
+    float ga[8], be[8], mu[8], rs[8], mA[8], mB[8], cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int g = (c0 + e) / gs;
+        ga[e] = gamma[c0 + e]; be[e] = beta[c0 + e];
+        mu[e] = s_mr[g * 4]; rs[e] = s_mr[g * 4 + 1]; mA[e] = s_mr[g * 4 + 2]; mB[e] = s_mr[g * 4 + 3];
+        cs[e] = 0.f;
+    }
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
+    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
+        const size_t o = ((size_t)n * HW + pp) * C + c0;
+        const bf8 xv = load8(x + o);
+        const bf8 gv = load8(da + o);
+        bf8 r;
+        if (addend) r = load8(addend + o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float xh = (xv.v[e] - mu[e]) * rs[e];
+            const float dy = (xh * ga[e] + be[e] > 0.f) ? gv.v[e] : 0.f;
+            float d = rs[e] * (dy * ga[e] - mA[e] - xh * mB[e]);
+            if (addend) d += r.v[e];
+            r.v[e] = d;
+        }
+        store8(dx + o, r);
+        if (colsum) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cs[e] += r.v[e];
+        }
+    }
+    if (colsum) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[c0 + e], cs[e]);
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += kT) atomicAdd(&colsum[c], s_cs[c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pooling / up-sampling
+// y[n,h,w,:] = max over the 2x2 window of x; statistics of y; x is [N,2H,2W,C].
+__global__ void __launch_bounds__(kT) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int H, int W, int C, int ppb,
+                                                         __nv_bfloat16* __restrict__ y, float* __restrict__ stats_out, int G_out) {
+    __shared__ float s_st[64];
+    const int n = blockIdx.y, HW = H * W;
+    if (threadIdx.x < 64) s_st[threadIdx.x] = 0.f;
+    __syncthreads();
+    const Walk w = make_walk(C);
+    const int c0 = w.cv * 8;
+    float st[4] = {0.f, 0.f, 0.f, 0.f};
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
+    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
+        const int h = pp / W, ww = pp % W;
+        const __nv_bfloat16* src = x + (((size_t)n * 2 * H + 2 * h) * 2 * W + 2 * ww) * C + c0;
+        const bf8 a = load8(src), b = load8(src + C), c = load8(src + (size_t)2 * W * C), d = load8(src + (size_t)2 * W * C + C);
+        bf8 r;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r.v[e] = fmaxf(fmaxf(a.v[e], b.v[e]), fmaxf(c.v[e], d.v[e]));
+        store8(y + ((size_t)n * HW + pp) * C + c0, r);
+        if (stats_out) stats_accum(st, r, C / G_out);
+    }
+    if (stats_out) {
+        stats_flush(s_st, st, c0, C / G_out);
+        __syncthreads();
+        if (threadIdx.x < G_out * 2) atomicAdd(&stats_out[(size_t)n * G_out * 2 + threadIdx.x], s_st[threadIdx.x]);
+    }
+}
+
+// dx[n,2h+i,2w+j,:] (+)= dy[n,h,w,:] for the FIRST maximal element of the window in (0,0),(0,1),(1,0),(1,1) order
+// (ATen's max_pool2d backward routes to the first maximum), zero elsewhere; optional addend (another gradient
+// flowing into x) and column sum.
+__global__ void __launch_bounds__(kT) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                         const __nv_bfloat16* __restrict__ addend, int H, int W, int C, int ppb,
+                                                         __nv_bfloat16* __restrict__ dx, float* __restrict__ colsum) {
+    __shared__ float s_cs[256];
+    const int n = blockIdx.y, HW = H * W;
+    if (threadIdx.x < 256) s_cs[threadIdx.x] = 0.f;
+    __syncthreads();
+    const Walk w = make_walk(C);
+    const int c0 = w.cv * 8;
+    float cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
+    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
+        const int h = pp / W, ww = pp % W;
+        const size_t base = (((size_t)n * 2 * H + 2 * h) * 2 * W + 2 * ww) * C + c0;
+        const size_t offs[4] = {0, (size_t)C, (size_t)2 * W * C, (size_t)2 * W * C + C};
+        bf8 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = load8(x + base + offs[q]);
+        const bf8 g = load8(dy + ((size_t)n * HW + pp) * C + c0);
+        bf8 o[4];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int best = 0;
+            float bv = v[0].v[e];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) if (v[q].v[e] > bv) { bv = v[q].v[e]; best = q; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q].v[e] = (q == best) ? g.v[e] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (addend) {
+                const bf8 r = load8(addend + base + offs[q]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[q].v[e] += r.v[e];
+            }
+            store8(dx + base + offs[q], o[q]);
+            if (colsum) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) cs[e] += o[q].v[e];
+            }
+        }
+    }
+    if (colsum) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[c0 + e], cs[e]);
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += kT) atomicAdd(&colsum[c], s_cs[c]);
+    }
+}
+
+// y = up1 + bilinear_x2(low), align_corners=False: src = (dst + 0.5)/2 - 0.5 clamped -> weights (0.75, 0.25);
+// y is [N,2h,2w,C], low is [N,h,w,C].
+__device__ __forceinline__ void up_taps(int d, int n_src, int& i0, int& i1, float& w0, float& w1) {
+    // d even: src = d/2 - 0.25 -> i0 = d/2 - 1 (w 0.25), i1 = d/2 (w 0.75); d odd: i0 = d/2 (0.75), i1 = d/2 + 1 (0.25)
+    const int hlf = d >> 1;
+    if (d & 1) { i0 = hlf; i1 = min(hlf + 1, n_src - 1); w0 = 0.75f; w1 = 0.25f; }
+    else { i0 = max(hlf - 1, 0); i1 = hlf; w0 = 0.25f; w1 = 0.75f; }
+}
+
+__global__ void __launch_bounds__(kT) upsample_add_fwd_kernel(const __nv_bfloat16* __restrict__ up1, const __nv_bfloat16* __restrict__ low,
+                                                              int h, int w_, int C, int ppb, __nv_bfloat16* __restrict__ y,
+                                                              float* __restrict__ stats_out, int G_out) {
+    __shared__ float s_st[64];
+    const int n = blockIdx.y, H = 2 * h, W = 2 * w_, HW = H * W;
+    if (threadIdx.x < 64) s_st[threadIdx.x] = 0.f;
+    __syncthreads();
+    const Walk w = make_walk(C);
+    const int c0 = w.cv * 8;
+    float st[4] = {0.f, 0.f, 0.f, 0.f};
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
+    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
+        const int yy = pp / W, xx = pp % W;
+        int y0, y1, x0, x1;
+        float wy0, wy1, wx0, wx1;
+        up_taps(yy, h, y0, y1, wy0, wy1);
+        up_taps(xx, w_, x0, x1, wx0, wx1);
+        const __nv_bfloat16* lb = low + (size_t)n * h * w_ * C + c0;
+        const bf8 a = load8(lb + ((size_t)y0 * w_ + x0) * C), b = load8(lb + ((size_t)y0 * w_ + x1) * C);
+        const bf8 c = load8(lb + ((size_t)y1 * w_ + x0) * C), d = load8(lb + ((size_t)y1 * w_ + x1) * C);
+        bf8 r = load8(up1 + ((size_t)n * HW + pp) * C + c0);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            r.v[e] += wy0 * (wx0 * a.v[e] + wx1 * b.v[e]) + wy1 * (wx0 * c.v[e] + wx1 * d.v[e]);
+        store8(y + ((size_t)n * HW + pp) * C + c0, r);
+        if (stats_out) stats_accum(st, r, C / G_out);
+    }
+    if (stats_out) {
+        stats_flush(s_st, st, c0, C / G_out);
+        __syncthreads();
+        if (threadIdx.x < G_out * 2) atomicAdd(&stats_out[(size_t)n * G_out * 2 + threadIdx.x], s_st[threadIdx.x]);
+    }
+}
+
+// dlow[n,i,j,:] = sum over the (up to 4x4) fine pixels that read (i,j) of weight * dy  (transpose of the above), + column sum
+__global__ void __launch_bounds__(kT) upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int h, int w_, int C, int ppb,
+                                                          __nv_bfloat16* __restrict__ dlow, float* __restrict__ colsum) {
+    __shared__ float s_cs[256];
+    const int n = blockIdx.y, hw = h * w_, H = 2 * h, W = 2 * w_;
+    if (threadIdx.x < 256) s_cs[threadIdx.x] = 0.f;
+    __syncthreads();
+    const Walk w = make_walk(C);
+    const int c0 = w.cv * 8;
+    float cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, hw);
+    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
+        const int i = pp / w_, j = pp % w_;
+        bf8 acc;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc.v[e] = 0.f;
+        for (int yy = max(2 * i - 2, 0); yy <= min(2 * i + 3, H - 1); ++yy) {
+            int y0, y1; float wy0, wy1;
+            up_taps(yy, h, y0, y1, wy0, wy1);
+            const float wy = (y0 == i ? wy0 : 0.f) + (y1 == i ? wy1 : 0.f);
+            if (wy == 0.f) continue;
+            for (int xx = max(2 * j - 2, 0); xx <= min(2 * j + 3, W - 1); ++xx) {
+                int x0, x1; float wx0, wx1;
+                up_taps(xx, w_, x0, x1, wx0, wx1);
+                const float wx = (x0 == j ? wx0 : 0.f) + (x1 == j ? wx1 : 0.f);
+                if (wx == 0.f) continue;
+                const bf8 g = load8(dy + (((size_t)n * H + yy) * W + xx) * C + c0);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc.v[e] += wy * wx * g.v[e];
+            }
+        }
+        store8(dlow + ((size_t)n * hw + pp) * C + c0, acc);
+        if (colsum) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cs[e] += acc.v[e];
+        }
+    }
+    if (colsum) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[c0 + e], cs[e]);
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += kT) atomicAdd(&colsum[c], s_cs[c]);
+    }
+}
+
+// y = a + b (+ c), optional statistics of y and column sum of y (used both for activations and for gradient fan-in)
+__global__ void __launch_bounds__(kT) add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                 const __nv_bfloat16* __restrict__ c, int HW, int C, int ppb, __nv_bfloat16* __restrict__ y,
+                                                 float* __restrict__ stats_out, int G_out, float* __restrict__ colsum) {
+    __shared__ float s_st[64];
+    __shared__ float s_cs[256];
+    const int n = blockIdx.y;
+    if (threadIdx.x < 64) s_st[threadIdx.x] = 0.f;
+    if (threadIdx.x < 256) s_cs[threadIdx.x] = 0.f;
+    __syncthreads();
+    const Walk w = make_walk(C);
+    const int c0 = w.cv * 8;
+    float cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+    float st[4] = {0.f, 0.f, 0.f, 0.f};
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
+    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
+        const size_t o = ((size_t)n * HW + pp) * C + c0;
+        bf8 r = load8(a + o);
+        const bf8 s = load8(b + o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r.v[e] += s.v[e];
+        if (c) {
+            const bf8 t = load8(c + o);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) r.v[e] += t.v[e];
+        }
+        store8(y + o, r);
+        if (stats_out) stats_accum(st, r, C / G_out);
+        if (colsum) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cs[e] += r.v[e];
+        }
+    }
+    if (stats_out) stats_flush(s_st, st, c0, C / G_out);
+    __syncthreads();
+    if (stats_out && threadIdx.x < G_out * 2) atomicAdd(&stats_out[(size_t)n * G_out * 2 + threadIdx.x], s_st[threadIdx.x]);
+    if (colsum) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[c0 + e], cs[e]);
+        __syncthreads();
+        for (int ch = threadIdx.x; ch < C; ch += kT) atomicAdd(&colsum[ch], s_cs[ch]);
+    }
+}
+
+// column sum of a bf16 NHWC tensor (bias gradient when no producer kernel could fuse it)
+__global__ void __launch_bounds__(kT) colsum_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int ppb, float* __restrict__ colsum) {
+    __shared__ float s_cs[256];
+    const int n = blockIdx.y;
+    if (threadIdx.x < 256) s_cs[threadIdx.x] = 0.f;
+    __syncthreads();
+    const Walk w = make_walk(C);
+    const int c0 = w.cv * 8;
+    float cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
+    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
+        const bf8 r = load8(x + ((size_t)n * HW + pp) * C + c0);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cs[e] += r.v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[c0 + e], cs[e]);
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < C; ch += kT) atomicAdd(&colsum[ch], s_cs[ch]);
+}
+
+// ------------------------------------------------------------------------------------------------ stem: 5x5 stride-2 conv, Cin = 1
+// y[n,oh,ow,co] = b[co] + sum_{kh,kw} img[n, 2oh+kh-2, 2ow+kw-2] * w[co,kh,kw];  img fp32 [N,S,S]; y bf16 [N,S/2,S/2,64] + stats.
+__global__ void __launch_bounds__(kT) stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ wgt,
+                                                           const float* __restrict__ bias, int S, int ppb, __nv_bfloat16* __restrict__ y,
+                                                           float* __restrict__ stats_out, int G_out) {
+    __shared__ float s_w[25 * 64];          // [tap][co]
+    __shared__ float s_b[64];
+    __shared__ float s_st[64];
+    const int n = blockIdx.y, O = S / 2, HW = O * O;
+    for (int i = threadIdx.x; i < 25 * 64; i += kT) s_w[i] = wgt[(i % 64) * 25 + i / 64];
+    if (threadIdx.x < 64) { s_b[threadIdx.x] = bias[threadIdx.x]; s_st[threadIdx.x] = 0.f; }
+    __syncthreads();
+    const int cv = threadIdx.x % 8, r = threadIdx.x / 8;        // 8 channel vectors (64 ch), 32 pixel rows
+    const int c0 = cv * 8;
+    float st[4] = {0.f, 0.f, 0.f, 0.f};
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
+    for (int pp = blockIdx.x * ppb + r; pp < p_end; pp += kT / 8) {
+        const int oh = pp / O, ow = pp % O;
+        bf8 acc;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc.v[e] = s_b[c0 + e];
+#pragma unroll
+        for (int kh = 0; kh < 5; ++kh) {
+            const int ih = 2 * oh + kh - 2;
+            if (ih < 0 || ih >= S) continue;
+#pragma unroll
+            for (int kw = 0; kw < 5; ++kw) {
+                const int iw = 2 * ow + kw - 2;
+                if (iw < 0 || iw >= S) continue;
+                const float v = __ldg(img + ((size_t)n * S + ih) * S + iw);
+                const float* wp = s_w + (kh * 5 + kw) * 64 + c0;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc.v[e] += v * wp[e];
+            }
+        }
+        store8(y + ((size_t)n * HW + pp) * 64 + c0, acc);
+        if (stats_out) stats_accum(st, acc, 64 / G_out);
+    }
+    if (stats_out) {
+        stats_flush(s_st, st, c0, 64 / G_out);
+        __syncthreads();
+        if (threadIdx.x < G_out * 2) atomicAdd(&stats_out[(size_t)n * G_out * 2 + threadIdx.x], s_st[threadIdx.x]);
+    }
+}
+
+// dW[co,kh,kw] = sum_{n,oh,ow} dy[n,oh,ow,co] * img[n,2oh+kh-2,2ow+kw-2];  db[co] = sum dy.   dw: fp32 [64,25], db: [64]
+__global__ void __launch_bounds__(kT) stem_conv_wgrad_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ dy,
+                                                             int S, int ppb, float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float s_dw[26 * 64];         // [tap | bias][co]
+    const int n = blockIdx.y, O = S / 2, HW = O * O;
+    for (int i = threadIdx.x; i < 26 * 64; i += kT) s_dw[i] = 0.f;
+    __syncthreads();
+    const int cv = threadIdx.x % 8, r = threadIdx.x / 8;
+    const int c0 = cv * 8;
+    float acc[26][8];
+#pragma unroll
+    for (int t = 0; t < 26; ++t)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
+    for (int pp = blockIdx.x * ppb + r; pp < p_end; pp += kT / 8) {
+        const int oh = pp / O, ow = pp % O;
+        const bf8 g = load8(dy + ((size_t)n * HW + pp) * 64 + c0);
+#pragma unroll
+        for (int kh = 0; kh < 5; ++kh) {
+            const int ih = 2 * oh + kh - 2;
+#pragma unroll
+            for (int kw = 0; kw < 5; ++kw) {
+                const int iw = 2 * ow + kw - 2;
+                const float v = (ih >= 0 && ih < S && iw >= 0 && iw < S) ? __ldg(img + ((size_t)n * S + ih) * S + iw) : 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[kh * 5 + kw][e] += v * g.v[e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[25][e] += g.v[e];
+    }
+#pragma unroll
+    for (int t = 0; t < 26; ++t)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&s_dw[t * 64 + c0 + e], acc[t][e]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 25 * 64; i += kT) atomicAdd(&dw[(i % 64) * 25 + i / 64], s_dw[i]);
+    if (threadIdx.x < 64) atomicAdd(&db[threadIdx.x], s_dw[25 * 64 + threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------ layout / weights / optimiser
+// fp32 NCHW [N,C,H,W] -> bf16 NHWC [N,H,W,Cp] (channels >= C zero-filled)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, int HW, int Cp, __nv_bfloat16* __restrict__ y) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? x[((size_t)n * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < HW && c < Cp) y[((size_t)n * HW + p) * Cp + c] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+}
+
+// bf16 NHWC [N,H,W,C] -> fp32 NCHW [N,C,H,W]
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int N, int C, int HW, float* __restrict__ y) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (p < HW && c < C) ? __bfloat162float(x[((size_t)n * HW + p) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        if (c < C && p < HW) y[((size_t)n * C + c) * HW + p] = tile[threadIdx.x][i];
+    }
+}
+
+// fp32 master weight [Cout,Cin,kh,kw] -> bf16 forward layout wf[tap][cout_pad][cin_pad] and (optionally) the
+// data-gradient layout wb[tap'][cin_pad_rows][cout_pad_cols] = w[co][ci][K-1-kh][K-1-kw]  (flipped + transposed)
+__global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int cout_pad, int cin_pad,
+                                    int b_rows, int b_cols, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wb) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nf = (long)taps * cout_pad * cin_pad;
+    if (i < nf) {
+        const int ci = (int)(i % cin_pad), co = (int)((i / cin_pad) % cout_pad), tap = (int)(i / ((long)cin_pad * cout_pad));
+        const float v = (co < Cout && ci < Cin) ? w[((size_t)co * Cin + ci) * taps + tap] : 0.f;
+        wf[i] = __float2bfloat16(v);
+    }
+    const long nb = (long)taps * b_rows * b_cols;
+    if (wb && i < nb) {
+        const int co = (int)(i % b_cols), ci = (int)((i / b_cols) % b_rows), tap = (int)(i / ((long)b_cols * b_rows));
+        const float v = (co < Cout && ci < Cin) ? w[((size_t)co * Cin + ci) * taps + (taps - 1 - tap)] : 0.f;
+        wb[i] = __float2bfloat16(v);
+    }
+}
+
+// dW fp32 [tap][Cout][Cin] (tensor-core accumulation layout) -> grad fp32 [Cout][Cin][kh][kw] (the reference layout)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Cout, int Cin, int taps, int cout_ld, int cin_ld,
+                                    float* __restrict__ grad) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)Cout * Cin * taps) return;
+    const int tap = (int)(i % taps), ci = (int)((i / taps) % Cin), co = (int)(i / ((long)taps * Cin));
+    grad[i] = dw[((size_t)tap * cout_ld + co) * cin_ld + ci];
+}
+
+// Adam with L2 weight decay folded into the gradient (torch.optim.Adam semantics, engine.py:95-97), flat buffers.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
+                            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float pi = p[i];
+    const float gi = g[i] * gscale + wd * pi;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
+inline int pick_ppb(int HW, int N, int rows) {
+    // pixels per block: aim for >= 2 waves over 148 SMs x 8 resident CTAs, at least 4 iterations per thread row
+    int ppb = HW;
+    while (ppb > rows * 4 && (long)N * ((HW + ppb - 1) / ppb) < 2L * SH_NUM_SMS * 8) ppb = (ppb + 1) / 2;
+    return ppb;
+}
+
+}  // namespace
+
+#define NHWC_CHECK(name)                                                                                    \
+    SH_REQUIRE(C % 8 == 0 && C <= 256 && kT % (C / 8) == 0, name ": C must be a multiple of 8, <= 256 and divide 2048")
+
+SH_EXPORT int sh_gn_relu_fwd(const void* x, const void* stats_in, const void* gamma, const void* beta, int N, int HW, int C,
+                              int G, float eps, void* y, void* stats_out, int G_out, void* stream) {
+    SH_REQUIRE(x && stats_in && gamma && beta && y, "sh_gn_relu_fwd: null pointer");
+    NHWC_CHECK("sh_gn_relu_fwd");
+    SH_REQUIRE(G >= 1 && G <= 32 && C % G == 0 && (!stats_out || (G_out >= 1 && G_out <= 32 && C % G_out == 0 && (C / G_out) % 4 == 0)),
+               "sh_gn_relu_fwd: bad grouping");
+    if (N == 0) return SH_OK;
+    const int ppb = pick_ppb(HW, N, kT / (C / 8));
+    dim3 grid(sh_div_up(HW, ppb), N);
+    gn_relu_fwd_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const float*)stats_in, (const float*)gamma,
+                                                              (const float*)beta, HW, C, G, ppb, eps, (__nv_bfloat16*)y,
+                                                              (float*)stats_out, G_out);
+    SH_CHECK_LAUNCH("gn_relu_fwd_kernel");
+    return SH_OK;
+}
+
+// red: fp32 [N,G,2] scratch (zeroed here); dgamma/dbeta accumulated (caller zeroes once per step)
+SH_EXPORT int sh_gn_relu_bwd(const void* da, const void* x, const void* stats_in, const void* gamma, const void* beta,
+                              const void* addend, int N, int HW, int C, int G, float eps, void* red, void* dgamma, void* dbeta,
+                              void* dx, void* colsum, void* stream) {
+    SH_REQUIRE(da && x && stats_in && gamma && beta && red && dgamma && dbeta && dx, "sh_gn_relu_bwd: null pointer");
+    NHWC_CHECK("sh_gn_relu_bwd");
+    SH_REQUIRE(G >= 1 && G <= 32 && C % G == 0 && (C / G) % 4 == 0, "sh_gn_relu_bwd: bad grouping");
+    if (N == 0) return SH_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    SH_CUDA(cudaMemsetAsync(red, 0, (size_t)N * G * 2 * sizeof(float), st));
+    const int ppb = pick_ppb(HW, N, kT / (C / 8));
+    dim3 grid(sh_div_up(HW, ppb), N);
+    gn_relu_bwd_reduce_kernel<<<grid, kT, 0, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)x, (const float*)stats_in,
+                                                   (const float*)gamma, (const float*)beta, HW, C, G, ppb, eps, (float*)red,
+                                                   (float*)dgamma, (float*)dbeta);
+    SH_CHECK_LAUNCH("gn_relu_bwd_reduce_kernel");
+    gn_relu_bwd_apply_kernel<<<grid, kT, 0, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)x, (const float*)stats_in,
+                                                  (const float*)red, (const float*)gamma, (const float*)beta,
+                                                  (const __nv_bfloat16*)addend, HW, C, G, ppb, eps, (__nv_bfloat16*)dx,
+                                                  (float*)colsum);
+    SH_CHECK_LAUNCH("gn_relu_bwd_apply_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_maxpool_fwd(const void* x, int N, int H, int W, int C, void* y, void* stats_out, int G_out, void* stream) {
+    SH_REQUIRE(x && y, "sh_maxpool_fwd: null pointer");
+    NHWC_CHECK("sh_maxpool_fwd");
+    if (N == 0) return SH_OK;
+    const int ppb = pick_ppb(H * W, N, kT / (C / 8));
+    dim3 grid(sh_div_up(H * W, ppb), N);
+    maxpool_fwd_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, H, W, C, ppb, (__nv_bfloat16*)y,
+                                                              (float*)stats_out, G_out);
+    SH_CHECK_LAUNCH("maxpool_fwd_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_maxpool_bwd(const void* dy, const void* x, const void* addend, int N, int H, int W, int C, void* dx,
+                              void* colsum, void* stream) {
+    SH_REQUIRE(dy && x && dx, "sh_maxpool_bwd: null pointer");
+    NHWC_CHECK("sh_maxpool_bwd");
+    if (N == 0) return SH_OK;
+    const int ppb = pick_ppb(H * W, N, kT / (C / 8));
+    dim3 grid(sh_div_up(H * W, ppb), N);
+    maxpool_bwd_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                                              (const __nv_bfloat16*)addend, H, W, C, ppb, (__nv_bfloat16*)dx,
+                                                              (float*)colsum);
+    SH_CHECK_LAUNCH("maxpool_bwd_kernel");
+    return SH_OK;
+}
+
+// y[N,2h,2w,C] = up1 + bilinear_x2(low[N,h,w,C])
+SH_EXPORT int sh_upsample_add_fwd(const void* up1, const void* low, int N, int h, int w, int C, void* y, void* stats_out,
+                                   int G_out, void* stream) {
+    SH_REQUIRE(up1 && low && y, "sh_upsample_add_fwd: null pointer");
+    NHWC_CHECK("sh_upsample_add_fwd");
+    if (N == 0) return SH_OK;
+    const int ppb = pick_ppb(4 * h * w, N, kT / (C / 8));
+    dim3 grid(sh_div_up(4 * h * w, ppb), N);
+    upsample_add_fwd_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)up1, (const __nv_bfloat16*)low, h, w, C, ppb,
+                                                                   (__nv_bfloat16*)y, (float*)stats_out, G_out);
+    SH_CHECK_LAUNCH("upsample_add_fwd_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_upsample_bwd(const void* dy, int N, int h, int w, int C, void* dlow, void* colsum, void* stream) {
+    SH_REQUIRE(dy && dlow, "sh_upsample_bwd: null pointer");
+    NHWC_CHECK("sh_upsample_bwd");
+    if (N == 0) return SH_OK;
+    const int ppb = pick_ppb(h * w, N, kT / (C / 8));
+    dim3 grid(sh_div_up(h * w, ppb), N);
+    upsample_bwd_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, h, w, C, ppb, (__nv_bfloat16*)dlow,
+                                                               (float*)colsum);
+    SH_CHECK_LAUNCH("upsample_bwd_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_add(const void* a, const void* b, const void* c, int N, int HW, int C, void* y, void* stats_out, int G_out,
+                      void* colsum, void* stream) {
+    SH_REQUIRE(a && b && y, "sh_add: null pointer");
+    NHWC_CHECK("sh_add");
+    if (N == 0) return SH_OK;
+    const int ppb = pick_ppb(HW, N, kT / (C / 8));
+    dim3 grid(sh_div_up(HW, ppb), N);
+    add_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)c, HW, C,
+                                                      ppb, (__nv_bfloat16*)y, (float*)stats_out, G_out, (float*)colsum);
+    SH_CHECK_LAUNCH("add_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_colsum(const void* x, int N, int HW, int C, void* colsum, void* stream) {
+    SH_REQUIRE(x && colsum, "sh_colsum: null pointer");
+    NHWC_CHECK("sh_colsum");
+    if (N == 0) return SH_OK;
+    const int ppb = pick_ppb(HW, N, kT / (C / 8));
+    dim3 grid(sh_div_up(HW, ppb), N);
+    colsum_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, HW, C, ppb, (float*)colsum);
+    SH_CHECK_LAUNCH("colsum_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_stem_conv_fwd(const void* img, const void* w, const void* b, int N, int S, void* y, void* stats_out, int G_out,
+                                void* stream) {
+    SH_REQUIRE(img && w && b && y, "sh_stem_conv_fwd: null pointer");
+    SH_REQUIRE(S % 2 == 0 && S >= 2, "sh_stem_conv_fwd: S must be even");
+    if (N == 0) return SH_OK;
+    const int HW = (S / 2) * (S / 2);
+    const int ppb = pick_ppb(HW, N, 32);
+    dim3 grid(sh_div_up(HW, ppb), N);
+    stem_conv_fwd_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const float*)img, (const float*)w, (const float*)b, S, ppb,
+                                                                (__nv_bfloat16*)y, (float*)stats_out, G_out);
+    SH_CHECK_LAUNCH("stem_conv_fwd_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_stem_conv_wgrad(const void* img, const void* dy, int N, int S, void* dw, void* db, void* stream) {
+    SH_REQUIRE(img && dy && dw && db, "sh_stem_conv_wgrad: null pointer");
+    if (N == 0) return SH_OK;
+    const int HW = (S / 2) * (S / 2);
+    int ppb = HW;
+    while (ppb > 256 && (long)N * ((HW + ppb - 1) / ppb) < 2L * SH_NUM_SMS) ppb = (ppb + 1) / 2;
+    dim3 grid(sh_div_up(HW, ppb), N);
+    stem_conv_wgrad_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const float*)img, (const __nv_bfloat16*)dy, S, ppb, (float*)dw,
+                                                                  (float*)db);
+    SH_CHECK_LAUNCH("stem_conv_wgrad_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_nchw_to_nhwc(const void* x, int N, int C, int HW, int Cp, void* y, void* stream) {
+    SH_REQUIRE(x && y && Cp >= C, "sh_nchw_to_nhwc: bad arguments");
+    if (N == 0) return SH_OK;
+    dim3 grid(sh_div_up(HW, 32), sh_div_up(Cp, 32), N), block(32, 8);
+    nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const float*)x, N, C, HW, Cp, (__nv_bfloat16*)y);
+    SH_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_nhwc_to_nchw(const void* x, int N, int C, int HW, void* y, void* stream) {
+    SH_REQUIRE(x && y, "sh_nhwc_to_nchw: bad arguments");
+    if (N == 0) return SH_OK;
+    dim3 grid(sh_div_up(HW, 32), sh_div_up(C, 32), N), block(32, 8);
+    nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, C, HW, (float*)y);
+    SH_CHECK_LAUNCH("nhwc_to_nchw_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_pack_weights(const void* w, int Cout, int Cin, int taps, int cout_pad, int cin_pad, int b_rows, int b_cols,
+                               void* wf, void* wb, void* stream) {
+    SH_REQUIRE(w && wf, "sh_pack_weights: null pointer");
+    long n = (long)taps * cout_pad * cin_pad;
+    if (wb && (long)taps * b_rows * b_cols > n) n = (long)taps * b_rows * b_cols;
+    pack_weights_kernel<<<sh_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)w, Cout, Cin, taps, cout_pad, cin_pad,
+                                                                            b_rows, b_cols, (__nv_bfloat16*)wf, (__nv_bfloat16*)wb);
+    SH_CHECK_LAUNCH("pack_weights_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_unpack_wgrad(const void* dw, int Cout, int Cin, int taps, int cout_ld, int cin_ld, void* grad, void* stream) {
+    SH_REQUIRE(dw && grad, "sh_unpack_wgrad: null pointer");
+    const long n = (long)Cout * Cin * taps;
+    unpack_wgrad_kernel<<<sh_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)dw, Cout, Cin, taps, cout_ld, cin_ld,
+                                                                            (float*)grad);
+    SH_CHECK_LAUNCH("unpack_wgrad_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_adam_step(void* p, const void* g, void* m, void* v, long n, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, int step, float grad_scale, void* stream) {
+    SH_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "sh_adam_step: bad arguments");
+    if (n == 0) return SH_OK;
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    adam_kernel<<<sh_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>((float*)p, (const float*)g, (float*)m, (float*)v, n, lr, beta1,
+                                                                    beta2, eps, weight_decay, bc1, bc2, grad_scale);
+    SH_CHECK_LAUNCH("adam_kernel");
+    return SH_OK;
+}

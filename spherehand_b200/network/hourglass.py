@@ -1,0 +1,413 @@
+"""Stacked-hourglass network on the B200 kernels — drop-in for /root/reference/network/hourglass.py.
+
+`create_hourglass_network(num_outputs, num_stacks)` returns a module with the reference's parameter names and
+shapes (`conv1.weight (64,1,5,5)`, `layer1.0.bn1.weight`, `hg.0.hg.1.2.0.conv2.weight`, `res.0.0...`, `fc.0.0/.1`,
+`score.0`, `fc_.0`, `score_.0`; hourglass.py:89-120), so `pretrained/*.pth` load unchanged, and the reference's
+`forward(x) -> (list[score], list[latent])` (hourglass.py:147-173).  The nn.Conv2d / nn.GroupNorm children are
+parameter holders only: the arithmetic runs through the C ABI (tcgen05 implicit-GEMM convolutions, fused
+GroupNorm/ReLU/pool/up-sample kernels) on NHWC bf16 activations with fp32 accumulation, fp32 master weights and
+fp32 GroupNorm statistics.  Precision contract: bf16 operands => heat-maps within 2e-2 of the fp32 reference
+(tests/test_gpu_hourglass.py); everything downstream of the heat-maps is fp32.
+
+There is no CPU path: calling forward on CPU tensors raises.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+BF16 = torch.bfloat16
+
+
+def _ceil(x, m):
+    return (x + m - 1) // m * m
+
+
+class Bottleneck(nn.Module):
+    """Parameter holder for the pre-activation bottleneck (hourglass.py:7-41)."""
+    expansion = 2
+
+    def __init__(self, inplanes, planes, downsample=None):
+        super().__init__()
+        self.bn1 = nn.GroupNorm(16, inplanes)
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=1, bias=True)
+        self.bn2 = nn.GroupNorm(16, planes)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, padding=1, bias=True)
+        self.bn3 = nn.GroupNorm(16, planes)
+        self.conv3 = nn.Conv2d(planes, planes * 2, kernel_size=1, bias=True)
+        self.downsample = downsample
+
+
+class Hourglass(nn.Module):
+    """Parameter holder for one depth-`depth` hourglass (hourglass.py:44-66)."""
+
+    def __init__(self, planes, depth):
+        super().__init__()
+        self.depth = depth
+        levels = []
+        for i in range(depth):
+            n_res = 4 if i == 0 else 3
+            levels.append(nn.ModuleList([nn.Sequential(Bottleneck(planes * 2, planes)) for _ in range(n_res)]))
+        self.hg = nn.ModuleList(levels)
+
+
+class _Tensor:
+    """NHWC bf16 activation + the fp32 [N,16,2] statistics the consuming GroupNorm needs."""
+    __slots__ = ('buf', 'stats', 'H', 'W', 'C')
+
+    def __init__(self, buf, stats, H, W, C):
+        self.buf, self.stats, self.H, self.W, self.C = buf, stats, H, W, C
+
+
+class HourglassNet(nn.Module):
+    def __init__(self, num_stacks, num_outputs):
+        super().__init__()
+        self.num_stacks = num_stacks
+        self.num_outputs = num_outputs
+        self.num_feats = 128
+        ch = 256
+        # creation order follows hourglass.py:95-120 so that a seeded default init matches the reference's
+        self.conv1 = nn.Conv2d(1, 64, kernel_size=5, padding=2, stride=2, bias=True)
+        self.bn1 = nn.GroupNorm(4, 64)
+        self.layer1 = nn.Sequential(Bottleneck(64, 64, nn.Sequential(nn.Conv2d(64, 128, kernel_size=1, bias=True))))
+        self.layer2 = nn.Sequential(Bottleneck(128, 128, nn.Sequential(nn.Conv2d(128, 256, kernel_size=1, bias=True))))
+        self.layer3 = nn.Sequential(Bottleneck(256, 128))
+        hg, res, fc, score, fc_, score_ = [], [], [], [], [], []
+        for i in range(num_stacks):
+            hg.append(Hourglass(self.num_feats, 2))
+            res.append(nn.Sequential(Bottleneck(ch, self.num_feats)))
+            fc.append(nn.Sequential(nn.Conv2d(ch, ch, kernel_size=1, bias=True), nn.GroupNorm(16, ch)))   # (:138-145)
+            score.append(nn.Conv2d(ch, num_outputs, kernel_size=1, bias=True))
+            if i < num_stacks - 1:
+                fc_.append(nn.Conv2d(ch, ch, kernel_size=1, bias=True))
+                score_.append(nn.Conv2d(num_outputs, ch, kernel_size=1, bias=True))
+        self.hg = nn.ModuleList(hg)
+        self.res = nn.ModuleList(res)
+        self.fc = nn.ModuleList(fc)
+        self.score = nn.ModuleList(score)
+        self.fc_ = nn.ModuleList(fc_)
+        self.score_ = nn.ModuleList(score_)
+        self._flat = None
+        self._flat_grad = None
+        self._wcache = {}
+
+    # ------------------------------------------------------------------ flat parameter storage
+    def flatten_parameters(self):
+        """Re-home every parameter as a view of one flat fp32 buffer (one Adam launch, one gradient all-reduce)."""
+        params = list(self.parameters())
+        dev = params[0].device
+        if self._flat is not None and self._flat.device == dev and all(p.data_ptr() == q for p, q in zip(params, self._ptrs)):
+            return self._flat
+        total = sum(_ceil(p.numel(), 4) for p in params)
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        self._offsets = {}
+        for p in params:
+            n = p.numel()
+            flat[off:off + n].copy_(p.data.reshape(-1).float())
+            p.data = flat[off:off + n].view(p.shape)
+            self._offsets[id(p)] = (off, n)
+            off += _ceil(n, 4)
+        self._flat, self._flat_grad = flat, grad
+        self._ptrs = [p.data_ptr() for p in params]
+        self._wcache = {}
+        return flat
+
+    def grad_view(self, p):
+        off, n = self._offsets[id(p)]
+        return self._flat_grad[off:off + n].view(p.shape)
+
+    # ------------------------------------------------------------------ execution
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError('spherehand_b200 HourglassNet runs on CUDA (sm_100a) only; there is no CPU fallback')
+        if x.dim() == 3:
+            x = x.unsqueeze(1)
+        res = _HourglassFn.apply(self, x, *list(self.parameters()))
+        return list(res[:self.num_stacks]), list(res[self.num_stacks:])
+
+    def run_forward(self, x):
+        """x fp32 [N,S,S] or [N,1,S,S] -> (scores fp32 NCHW list, latents fp32 NCHW list); records the backward tape."""
+        self.flatten_parameters()
+        if x.dim() == 4:
+            x = x[:, 0]
+        x = x.contiguous().float()
+        N, S = x.shape[0], x.shape[-1]
+        ctx = _Run(self, N, x.device)
+        scores, latents = ctx.forward(x, S)
+        self._last_run = ctx
+        return scores, latents
+
+    def run_backward(self, grad_scores):
+        """grad_scores: list of fp32 [N,num_outputs,h,w] (or None) -> gradients accumulated into the flat grad buffer."""
+        self._flat_grad.zero_()
+        self._last_run.backward(grad_scores)
+        return self._flat_grad
+
+
+class _HourglassFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        scores, latents = net.run_forward(x)
+        ctx.net = net
+        ctx.n_scores = len(scores)
+        ctx.mark_non_differentiable(*latents)
+        return (*scores, *latents)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        net = ctx.net
+        gs = [g.contiguous() if g is not None else None for g in grads[:ctx.n_scores]]
+        net.run_backward(gs)
+        out = [net.grad_view(p).clone() for p in net.parameters()]
+        return (None, None, *out)
+
+
+class _Run:
+    """One forward pass: allocates activations, runs the kernels, and records closures for the backward."""
+
+    def __init__(self, net, N, device):
+        self.net, self.N, self.dev = net, N, device
+        self.tape = []
+        self.stats_pool = torch.zeros((160, N, 16, 2), device=device, dtype=torch.float32)
+        self.stats_used = 0
+
+    # -------------------------------------------------------------- helpers
+    def new_stats(self):
+        s = self.stats_pool[self.stats_used]
+        self.stats_used += 1
+        return s
+
+    def act(self, H, W, C, stats=True):
+        buf = torch.empty((self.N, H, W, C), device=self.dev, dtype=BF16)
+        return _Tensor(buf, self.new_stats() if stats else None, H, W, C)
+
+    def packed(self, conv, need_bwd=True):
+        """bf16 forward / data-gradient weight layouts of a conv, re-packed from the fp32 master every forward."""
+        Cout, Cin, k, _ = conv.weight.shape
+        taps = k * k
+        cout_pad = _ceil(Cout, 128) if Cout > 64 else 64
+        cin_pad = _ceil(Cin, 64) if Cin % 64 else Cin
+        if Cin == self.net.num_outputs:
+            cin_pad = 128
+        key = id(conv)
+        if key not in self.net._wcache:
+            wf = torch.empty((taps, cout_pad, cin_pad), device=self.dev, dtype=BF16)
+            # data-gradient GEMM: rows = Cin (padded to its N tile), cols = Cout (padded to a K multiple of 64)
+            b_rows = _ceil(Cin, 128) if Cin > 64 else 64
+            b_cols = _ceil(Cout, 64)
+            if Cout == self.net.num_outputs:
+                b_cols = 128
+            wb = torch.empty((taps, b_rows, b_cols), device=self.dev, dtype=BF16) if need_bwd else None
+            self.net._wcache[key] = (wf, wb, cout_pad, cin_pad, b_rows, b_cols)
+        wf, wb, cout_pad, cin_pad, b_rows, b_cols = self.net._wcache[key]
+        ops.pack_weights(conv.weight.data, Cout, Cin, taps, cout_pad, cin_pad, wf, wb, b_rows, b_cols)
+        return wf, wb, cout_pad, cin_pad, b_rows, b_cols
+
+    # -------------------------------------------------------------- layers
+    def conv(self, conv, a, a_C, out, residual=None, y_nchw=None, want_stats=True):
+        """out = conv(a) + bias (+ residual).  a: bf16 buffer [N,H,W,a_C]; out: _Tensor (or None with y_nchw)."""
+        net, N = self.net, self.N
+        Cout, Cin, k, _ = conv.weight.shape
+        taps = k * k
+        wf, wb, cout_pad, cin_pad, b_rows, b_cols = self.packed(conv)
+        H, W = (out.H, out.W) if out is not None else y_nchw.shape[-2:]
+        assert cin_pad == a_C, (cin_pad, a_C)
+        ops.conv_fwd(a, wf, conv.bias.data, N, H, W, a_C, Cout, cout_pad, taps,
+                     y=out.buf if out is not None else None, y_ld=out.C if out is not None else 0, y_nchw=y_nchw,
+                     residual=residual, stats=out.stats if (out is not None and want_stats) else None, groups=16)
+
+        def bwd(dout, dout_C, need_dx=True, dx_addend=None):
+            """dout: bf16 [N,H,W,dout_C] gradient of the conv output -> returns bf16 gradient w.r.t. `a`."""
+            ops.conv_wgrad(dout, a, N, H, W, a_C, Cin, dout_C, Cout, taps, net.grad_view(conv.weight))
+            if not need_dx:
+                return None
+            dx = torch.empty((N, H, W, a_C), device=self.dev, dtype=BF16)
+            # data gradient = the same implicit GEMM on flipped/transposed weights: "Cin" := dout_C, "Cout" := a_C
+            assert b_cols == dout_C, (b_cols, dout_C)
+            ops.conv_fwd(dout, wb, None, N, H, W, dout_C, a_C, b_rows, taps, y=dx, y_ld=a_C,
+                         residual=dx_addend)
+            return dx
+        return bwd
+
+    def gn_relu(self, x, gn, G=16, out_stats=False, G_out=16):
+        """a = relu(groupnorm(x)); returns (a buffer, [stats of a], backward closure)."""
+        N = self.N
+        a = torch.empty_like(x.buf)
+        st = self.new_stats() if out_stats else None
+        ops.gn_relu_fwd(x.buf, x.stats, gn.weight.data, gn.bias.data, N, x.H * x.W, x.C, G, a, st, G_out)
+        net = self.net
+
+        def bwd(da, addend=None, colsum=None):
+            red = torch.empty((N, G, 2), device=self.dev, dtype=torch.float32)
+            dx = torch.empty_like(x.buf)
+            ops.gn_relu_bwd(da, x.buf, x.stats, gn.weight.data, gn.bias.data, N, x.H * x.W, x.C, G, red,
+                            net.grad_view(gn.weight), net.grad_view(gn.bias), dx, addend, colsum)
+            return dx
+        return a, st, bwd
+
+    def bottleneck(self, blk, x):
+        """Pre-activation bottleneck (hourglass.py:23-41).  x: _Tensor with stats -> _Tensor with stats."""
+        net, N = self.net, self.N
+        planes = blk.conv1.weight.shape[0]
+        H, W = x.H, x.W
+        a1, _, gn1_b = self.gn_relu(x, blk.bn1)
+        t1 = self.act(H, W, planes)
+        c1_b = self.conv(blk.conv1, a1, x.C, t1)
+        a2, _, gn2_b = self.gn_relu(t1, blk.bn2)
+        t2 = self.act(H, W, planes)
+        c2_b = self.conv(blk.conv2, a2, planes, t2)
+        a3, _, gn3_b = self.gn_relu(t2, blk.bn3)
+        out = self.act(H, W, planes * 2)
+        if blk.downsample is not None:
+            res = self.act(H, W, planes * 2, stats=False)
+            d_b = self.conv(blk.downsample[0], x.buf, x.C, res, want_stats=False)
+            res_buf = res.buf
+        else:
+            d_b, res_buf = None, x.buf
+        c3_b = self.conv(blk.conv3, a3, planes, out, residual=res_buf)
+
+        def bwd(dout):
+            # bias gradients of conv3 (and of the downsample conv, which sees the same output gradient)
+            ops.colsum(dout, N, H * W, planes * 2, net.grad_view(blk.conv3.bias))
+            if d_b is not None:
+                net.grad_view(blk.downsample[0].bias).copy_(net.grad_view(blk.conv3.bias))
+            da3 = c3_b(dout, planes * 2)
+            dt2 = gn3_b(da3, colsum=net.grad_view(blk.conv2.bias))
+            da2 = c2_b(dt2, planes)
+            dt1 = gn2_b(da2, colsum=net.grad_view(blk.conv1.bias))
+            da1 = c1_b(dt1, planes)
+            dres = d_b(dout, planes * 2) if d_b is not None else dout
+            return gn1_b(da1, addend=dres)
+        return out, bwd
+
+    def hourglass(self, hgm, n, x):
+        """hourglass.py:68-82.  Returns (out, latent, backward)."""
+        N = self.N
+        lvl = hgm.hg[n - 1]
+        up1, up1_b = self.bottleneck(lvl[0][0], x)
+        pooled = self.act(x.H // 2, x.W // 2, x.C)
+        ops.maxpool_fwd(x.buf, N, pooled.H, pooled.W, x.C, pooled.buf, pooled.stats, 16)
+        low1, low1_b = self.bottleneck(lvl[1][0], pooled)
+        if n > 1:
+            low2, latent, low2_b = self.hourglass(hgm, n - 1, low1)
+        else:
+            low2, low2_b = self.bottleneck(lvl[3][0], low1)
+            latent = low2
+        low3, low3_b = self.bottleneck(lvl[2][0], low2)
+        out = self.act(x.H, x.W, x.C)
+        ops.upsample_add_fwd(up1.buf, low3.buf, N, low3.H, low3.W, x.C, out.buf, out.stats, 16)
+
+        def bwd(dout, dlatent=None):
+            dlow3 = torch.empty_like(low3.buf)
+            ops.upsample_bwd(dout, N, low3.H, low3.W, x.C, dlow3)
+            dlow2 = low3_b(dlow3)
+            dlow1 = low2_b(dlow2)
+            dpooled = low1_b(dlow1)
+            dx_a = up1_b(dout)
+            dx = torch.empty_like(x.buf)
+            ops.maxpool_bwd(dpooled, x.buf, N, pooled.H, pooled.W, x.C, dx, addend=dx_a)
+            return dx
+        return out, latent, bwd
+
+    # -------------------------------------------------------------- whole network
+    def forward(self, img, S):
+        net, N = self.net, self.N
+        K = net.num_outputs
+        self.img = img
+        H = S // 2
+        # stem: conv1 -> GroupNorm(4) -> ReLU (hourglass.py:153-155)
+        c1 = _Tensor(torch.empty((N, H, H, 64), device=self.dev, dtype=BF16),
+                     torch.zeros((N, 4, 2), device=self.dev, dtype=torch.float32), H, H, 64)
+        ops.stem_conv_fwd(img, net.conv1.weight.data, net.conv1.bias.data, N, S, c1.buf, c1.stats, 4)
+        x0_buf, x0_stats, stem_gn_b = self.gn_relu(c1, net.bn1, G=4, out_stats=True, G_out=16)
+        x0 = _Tensor(x0_buf, x0_stats, H, H, 64)
+        l1, l1_b = self.bottleneck(net.layer1[0], x0)
+        H2 = H // 2
+        p1 = self.act(H2, H2, 128)
+        ops.maxpool_fwd(l1.buf, N, H2, H2, 128, p1.buf, p1.stats, 16)
+        l2, l2_b = self.bottleneck(net.layer2[0], p1)
+        x, l3_b = self.bottleneck(net.layer3[0], l2)
+        h = H2
+        scores, latents, stack_b = [], [], []
+        for i in range(net.num_stacks):
+            y, latent, hg_b = self.hourglass(net.hg[i], 2, x)
+            y, res_b = self.bottleneck(net.res[i][0], y)
+            f = self.act(h, h, 256)
+            fc_b = self.conv(net.fc[i][0], y.buf, 256, f)
+            yf_buf, _, fcgn_b = self.gn_relu(f, net.fc[i][1])
+            score = torch.empty((N, K, h, h), device=self.dev, dtype=torch.float32)
+            last = i == net.num_stacks - 1
+            score_pad = None if last else _Tensor(torch.zeros((N, h, h, 128), device=self.dev, dtype=BF16), None, h, h, 128)
+            sc_b = self.conv(net.score[i], yf_buf, 256, score_pad, y_nchw=score, want_stats=False)
+            scores.append(score)
+            lat = torch.empty((N, 256, latent.H, latent.W), device=self.dev, dtype=torch.float32)
+            ops.nhwc_to_nchw(latent.buf, N, 256, latent.H * latent.W, lat)
+            latents.append(lat)
+            if not last:
+                # x <- x + fc_(y) + score_(score)   (hourglass.py:169-172), both adds in the conv epilogues
+                t = self.act(h, h, 256, stats=False)
+                fcu_b = self.conv(net.fc_[i], yf_buf, 256, t, residual=x.buf, want_stats=False)
+                xn = self.act(h, h, 256)
+                scu_b = self.conv(net.score_[i], score_pad.buf, 128, xn, residual=t.buf)
+            else:
+                fcu_b = scu_b = xn = None
+            stack_b.append((hg_b, res_b, fc_b, fcgn_b, sc_b, fcu_b, scu_b, x, h))
+            if not last:
+                x = xn
+
+        def backward(grad_scores):
+            dx_next = None            # gradient w.r.t. the input of the following stack
+            for i in reversed(range(net.num_stacks)):
+                hg_b, res_b, fc_b, fcgn_b, sc_b, fcu_b, scu_b, xin, hh = stack_b[i]
+                g = grad_scores[i]
+                dscore = torch.zeros((N, hh, hh, 128), device=self.dev, dtype=BF16)
+                if g is not None:
+                    ops.nchw_to_nhwc(g.contiguous().float(), N, K, hh * hh, 128, dscore)
+                dyf = None
+                if dx_next is not None:
+                    # bias gradients of fc_ and score_ see dx_next
+                    ops.colsum(dx_next, N, hh * hh, 256, net.grad_view(net.fc_[i].bias))
+                    net.grad_view(net.score_[i].bias).copy_(net.grad_view(net.fc_[i].bias))
+                    dsp = scu_b(dx_next, 256)                       # [N,h,h,128] gradient of the padded score copy
+                    tmp = torch.empty_like(dscore)
+                    ops.add(dscore, dsp, N, hh * hh, 128, tmp)
+                    dscore = tmp
+                    dyf = fcu_b(dx_next, 256)
+                ops.colsum(dscore, N, hh * hh, 128, self._tmp128())
+                net.grad_view(net.score[i].bias).copy_(self._tmp128()[:K])
+                dyf = sc_b(dscore, 128, dx_addend=dyf)
+                df = fcgn_b(dyf, colsum=net.grad_view(net.fc[i][0].bias))
+                dy = fc_b(df, 256)
+                dy = res_b(dy)
+                dxin = hg_b(dy)
+                if dx_next is not None:
+                    tmp = torch.empty_like(dxin)
+                    ops.add(dxin, dx_next, N, hh * hh, 256, tmp)
+                    dxin = tmp
+                dx_next = dxin
+            d = l3_b(dx_next)
+            d = l2_b(d)
+            dl1 = torch.empty_like(l1.buf)
+            ops.maxpool_bwd(d, l1.buf, N, H2, H2, 128, dl1)
+            dx0 = l1_b(dl1)
+            dc1 = stem_gn_b(dx0)
+            ops.stem_conv_wgrad(self.img, dc1, N, S, net.grad_view(net.conv1.weight), net.grad_view(net.conv1.bias))
+        self._backward = backward
+        return scores, latents
+
+    def _tmp128(self):
+        if not hasattr(self, '_t128'):
+            self._t128 = torch.zeros(128, device=self.dev, dtype=torch.float32)
+        return self._t128
+
+    def backward(self, grad_scores):
+        if hasattr(self, '_t128'):
+            self._t128.zero_()
+        self._backward(grad_scores)
+
+
+def create_hourglass_network(num_outputs, num_stacks=1):
+    """Same signature as the reference factory (hourglass.py:175-176)."""
+    return HourglassNet(num_stacks=num_stacks, num_outputs=num_outputs)

@@ -1,0 +1,218 @@
+"""GPU parity tests for the hourglass layer kernels and the whole network (run with -m gpu).
+
+Floating-point kernels: the comparison is against plain PyTorch fp32 (TF32 disabled) on the same operands —
+for single layers on operands already rounded to bf16 (so only accumulation order and the bf16 output rounding
+differ: tolerance 1e-2 of the tensor's max), for the whole network against the fp32 oracle / the golden fixtures
+of the reference (tolerance 2e-2 on heat-maps, 5e-2 on gradients: bf16 operand contract)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+BF16 = torch.bfloat16
+
+if torch.cuda.is_available():
+    from spherehand_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def nhwc(x):      # fp32 NCHW -> bf16 NHWC
+    return x.permute(0, 2, 3, 1).contiguous().to(BF16)
+
+
+def nchw(x):      # bf16 NHWC -> fp32 NCHW
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def stats_of(x_nhwc, G):
+    N, H, W, C = x_nhwc.shape
+    v = x_nhwc.float().reshape(N, H * W, G, C // G)
+    return torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1).contiguous()
+
+
+@pytest.mark.parametrize('N,H,Cin,Cout,taps', [(2, 32, 128, 128, 9), (3, 16, 256, 128, 1), (2, 64, 64, 64, 9), (5, 8, 128, 256, 1),
+                                               (4, 4, 128, 128, 9), (2, 32, 256, 82, 1), (2, 32, 64, 128, 1)])
+def test_conv_fwd_dgrad_wgrad(N, H, Cin, Cout, taps):
+    torch.manual_seed(N * 100 + H)
+    k = 3 if taps == 9 else 1
+    x = torch.randn(N, Cin, H, H, device=DEV).to(BF16).float()
+    w = (torch.randn(Cout, Cin, k, k, device=DEV) / (Cin * taps) ** 0.5)
+    b = torch.randn(Cout, device=DEV)
+    res = torch.randn(N, Cout, H, H, device=DEV).to(BF16).float()
+    wq = w.to(BF16).float()
+    ref = F.conv2d(x, wq, b, padding=k // 2) + res
+    cout_pad = (Cout + 127) // 128 * 128 if Cout > 64 else 64
+    y_ld = cout_pad if Cout % 8 else Cout
+    wf = torch.empty((taps, cout_pad, Cin), device=DEV, dtype=BF16)
+    b_rows = (Cin + 127) // 128 * 128 if Cin > 64 else 64
+    b_cols = (Cout + 63) // 64 * 64
+    wb = torch.empty((taps, b_rows, b_cols), device=DEV, dtype=BF16)
+    ops.pack_weights(w, Cout, Cin, taps, cout_pad, Cin, wf, wb, b_rows, b_cols)
+    y = torch.zeros((N, H, H, y_ld), device=DEV, dtype=BF16)
+    y32 = torch.empty((N, Cout, H, H), device=DEV)
+    G = 16 if Cout % 16 == 0 and 32 % (Cout // 16) == 0 else 0
+    st = torch.zeros((N, 16, 2), device=DEV)
+    use_res = Cout % 8 == 0
+    ops.conv_fwd(nhwc(x), wf, b, N, H, H, Cin, Cout, cout_pad, taps, y=y, y_ld=y_ld, y_nchw=y32,
+                 residual=nhwc(res) if use_res else None, stats=st if G else None, groups=16)
+    if not use_res:
+        ref = ref - res
+    torch.cuda.synchronize()
+    assert rel_err(y32.cpu(), ref.cpu()) < 2e-3                          # fp32 output: accumulation order only
+    assert rel_err(nchw(y)[:, :Cout].cpu(), ref.cpu()) < 1e-2            # bf16 output rounding
+    if y_ld > Cout:
+        assert (y[..., Cout:] == 0).all()
+    if G:
+        assert rel_err(st.cpu(), stats_of(y, 16).cpu()) < 1e-3           # statistics describe the stored tensor
+    # ---- data gradient: same kernel on flipped / transposed weights
+    dy = torch.randn(N, Cout, H, H, device=DEV).to(BF16).float()
+    dyp = torch.zeros((N, H, H, b_cols), device=DEV, dtype=BF16)
+    dyp[..., :Cout] = nhwc(dy)
+    dx = torch.empty((N, H, H, Cin), device=DEV, dtype=BF16)
+    ops.conv_fwd(dyp, wb, None, N, H, H, b_cols, Cin, b_rows, taps, y=dx, y_ld=Cin)
+    ref_dx = torch.nn.grad.conv2d_input(x.shape, wq, dy, padding=k // 2)
+    assert rel_err(nchw(dx).cpu(), ref_dx.cpu()) < 1e-2
+    # ---- weight gradient (reference layout [Cout,Cin,k,k]); fp32 atomics over the pixel split
+    dw = torch.zeros_like(w)
+    ops.conv_wgrad(dyp, nhwc(x), N, H, H, Cin, Cin, b_cols, Cout, taps, dw)
+    ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, padding=k // 2)
+    assert rel_err(dw.cpu(), ref_dw.cpu()) < 2e-3
+
+
+@pytest.mark.parametrize('N,H,C,G', [(3, 16, 128, 16), (2, 32, 256, 16), (2, 32, 64, 16), (2, 32, 64, 4)])
+def test_gn_relu_fwd_bwd(N, H, C, G):
+    torch.manual_seed(C + G)
+    x = (torch.randn(N, C, H, H, device=DEV) * 2 + 0.5).to(BF16).float().requires_grad_(True)
+    gamma = (torch.rand(C, device=DEV) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device=DEV) * 0.3).requires_grad_(True)
+    ref = F.relu(F.group_norm(x, G, gamma, beta))
+    da = torch.randn_like(ref).to(BF16).float()
+    add = torch.randn_like(ref).to(BF16).float()
+    ref.backward(da)
+    xh = nhwc(x.detach())
+    st = stats_of(xh, G)
+    y = torch.empty_like(xh)
+    st_out = torch.zeros((N, 16, 2), device=DEV)
+    ops.gn_relu_fwd(xh, st, gamma.detach(), beta.detach(), N, H * H, C, G, y, st_out, 16)
+    assert rel_err(nchw(y).cpu(), ref.detach().cpu()) < 1e-2
+    assert rel_err(st_out.cpu(), stats_of(y, 16).cpu()) < 1e-3
+    red = torch.empty((N, G, 2), device=DEV)
+    dg, db, cs = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dx = torch.empty_like(xh)
+    ops.gn_relu_bwd(nhwc(da), xh, st, gamma.detach(), beta.detach(), N, H * H, C, G, red, dg, db, dx, nhwc(add), cs)
+    assert rel_err(nchw(dx).cpu(), (x.grad + add).cpu()) < 1.5e-2
+    assert rel_err(dg.cpu(), gamma.grad.cpu()) < 1e-2 and rel_err(db.cpu(), beta.grad.cpu()) < 1e-2
+    assert rel_err(cs.cpu(), nchw(dx).sum(dim=(0, 2, 3)).cpu()) < 1e-3
+
+
+def test_pool_upsample_add_stem_adam():
+    torch.manual_seed(3)
+    N, H, C = 3, 16, 128
+    x = torch.randn(N, C, 2 * H, 2 * H, device=DEV).to(BF16).float().requires_grad_(True)
+    ref = F.max_pool2d(x, 2, 2)
+    y = torch.empty((N, H, H, C), device=DEV, dtype=BF16)
+    st = torch.zeros((N, 16, 2), device=DEV)
+    ops.maxpool_fwd(nhwc(x.detach()), N, H, H, C, y, st, 16)
+    assert torch.equal(nchw(y), ref.detach())
+    assert rel_err(st.cpu(), stats_of(y, 16).cpu()) < 1e-3
+    dy = torch.randn_like(ref).to(BF16).float()
+    ref.backward(dy)
+    dx = torch.empty((N, 2 * H, 2 * H, C), device=DEV, dtype=BF16)
+    ops.maxpool_bwd(nhwc(dy), nhwc(x.detach()), N, H, H, C, dx)
+    assert torch.equal(nchw(dx), x.grad)
+    # up-sample + add
+    low = torch.randn(N, C, H, H, device=DEV).to(BF16).float().requires_grad_(True)
+    up1 = torch.randn(N, C, 2 * H, 2 * H, device=DEV).to(BF16).float()
+    ref = up1 + F.interpolate(low, scale_factor=2, mode='bilinear', align_corners=False)
+    y2 = torch.empty((N, 2 * H, 2 * H, C), device=DEV, dtype=BF16)
+    ops.upsample_add_fwd(nhwc(up1), nhwc(low.detach()), N, H, H, C, y2)
+    assert rel_err(nchw(y2).cpu(), ref.detach().cpu()) < 1e-2
+    dy2 = torch.randn_like(ref).to(BF16).float()
+    ref.backward(dy2)
+    dlow = torch.empty((N, H, H, C), device=DEV, dtype=BF16)
+    cs = torch.zeros(C, device=DEV)
+    ops.upsample_bwd(nhwc(dy2), N, H, H, C, dlow, cs)
+    assert rel_err(nchw(dlow).cpu(), low.grad.cpu()) < 1e-2
+    assert rel_err(cs.cpu(), nchw(dlow).sum(dim=(0, 2, 3)).cpu()) < 1e-3
+    # add (3 operands) + colsum
+    a, b, c = [torch.randn(N, H, H, C, device=DEV).to(BF16) for _ in range(3)]
+    y3 = torch.empty_like(a)
+    ops.add(a, b, N, H * H, C, y3, c=c)
+    assert rel_err(y3.float().cpu(), (a.float() + b.float() + c.float()).cpu()) < 1e-2
+    cs2 = torch.zeros(C, device=DEV)
+    ops.colsum(a, N, H * H, C, cs2)
+    assert rel_err(cs2.cpu(), a.float().sum(dim=(0, 1, 2)).cpu()) < 1e-4
+    # stem conv 5x5 s2 + its weight gradient
+    S = 64
+    img = torch.randn(N, 1, S, S, device=DEV)
+    w = (torch.randn(64, 1, 5, 5, device=DEV) * 0.2).requires_grad_(True)
+    bias = torch.randn(64, device=DEV).requires_grad_(True)
+    ref = F.conv2d(img, w, bias, stride=2, padding=2)
+    ys = torch.empty((N, S // 2, S // 2, 64), device=DEV, dtype=BF16)
+    st4 = torch.zeros((N, 4, 2), device=DEV)
+    ops.stem_conv_fwd(img[:, 0].contiguous(), w.detach(), bias.detach(), N, S, ys, st4, 4)
+    assert rel_err(nchw(ys).cpu(), ref.detach().cpu()) < 1e-2
+    assert rel_err(st4.cpu(), stats_of(ys, 4).cpu()) < 1e-3
+    dys = torch.randn_like(ref).to(BF16).float()
+    ref.backward(dys)
+    dw, dbias = torch.zeros_like(w), torch.zeros_like(bias)
+    ops.stem_conv_wgrad(img[:, 0].contiguous(), nhwc(dys), N, S, dw, dbias)
+    assert rel_err(dw.cpu(), w.grad.cpu()) < 1e-3 and rel_err(dbias.cpu(), bias.grad.cpu()) < 1e-3
+    # layout conversions
+    t = torch.randn(N, 82, 8, 8, device=DEV)
+    tp = torch.empty((N, 8, 8, 128), device=DEV, dtype=BF16)
+    ops.nchw_to_nhwc(t, N, 82, 64, 128, tp)
+    assert torch.equal(tp[..., :82], nhwc(t)) and (tp[..., 82:] == 0).all()
+    back = torch.empty((N, 128, 8, 8), device=DEV)
+    ops.nhwc_to_nchw(tp, N, 128, 64, back)
+    assert torch.equal(back, nchw(tp))
+    # Adam == torch.optim.Adam(weight_decay) step for step
+    p = torch.randn(1000, device=DEV)
+    p_ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-3, weight_decay=1e-5)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(1000, device=DEV)
+        p_ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-5, step)
+        assert rel_err(p.cpu(), p_ref.detach().cpu()) < 1e-5
+
+
+@pytest.mark.parametrize('stacks', [1, 2])
+def test_hourglass_golden(stacks):
+    """Whole network, forward + backward, against the reference's own outputs (deterministic weights)."""
+    from spherehand_b200.network.hourglass import create_hourglass_network
+    from oracle.hourglass import det_state_dict, det_uniform
+    g = golden('hourglass_%dstack' % stacks)
+    net = create_hourglass_network(82, stacks).to(DEV)
+    net.load_state_dict(det_state_dict(82, stacks, seed=7))
+    x = torch.from_numpy(g['x']).to(DEV)
+    outs, lats = net(x)
+    errs = []
+    for i, o in enumerate(outs):
+        errs.append(rel_err(o.detach().cpu(), g['score%d' % i]))
+        errs.append(rel_err(lats[i].cpu(), g['latent%d' % i]))
+    print('hourglass %d-stack forward rel errs (score, latent per stack):' % stacks, ['%.4f' % e for e in errs])
+    assert max(errs) < 2e-2
+    gs = [torch.from_numpy(det_uniform(o.numel(), 100 + i).reshape(o.shape)).to(DEV) for i, o in enumerate(outs)]
+    sum((o * gg).sum() for o, gg in zip(outs, gs)).backward()
+    params = dict(net.named_parameters())
+    worst = {}
+    for k in g:
+        if k.startswith('grad.'):
+            worst[k[5:]] = rel_err(params[k[5:]].grad.cpu(), g[k])
+    norm_err = {}
+    for k in g:
+        if k.startswith('gradnorm.'):
+            norm_err[k[9:]] = abs(float(params[k[9:]].grad.double().norm()) / float(g[k]) - 1)
+    bad = sorted(norm_err.items(), key=lambda kv: -kv[1])[:5]
+    print('hourglass %d-stack grad rel errs:' % stacks, {k: '%.4f' % v for k, v in worst.items()})
+    print('worst grad-norm deviations:', bad)
+    assert max(worst.values()) < 5e-2
+    assert max(norm_err.values()) < 5e-2
