@@ -23,9 +23,10 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------------------------------------ library */
-int sh_abi_version(void);
+int sh_abi_version(void);          /* 2 */
 const char* sh_build_arch(void);      /* "sm_100a" */
 const char* sh_last_error(void);
+long sh_launch_count(void);          /* kernel launches issued through this library since load */
 
 /* ------------------------------------------------------------------------------------------------ R1: triangle rasteriser
  * Replaces depth_rasterization_cuda_forward + kernel, mesh/cuda_kernel/depth_rasterization_cuda_kernel.cu:18-134.
@@ -67,10 +68,12 @@ int sh_pose_losses_fwdbwd(const void* cam, const void* joints, int B, int V, int
 
 /* Replaces PoseVae.prior_loss (network/pose_vae.py:81-89).  x [M,123] (= xyz/100), eps [M,32] ~ N(0,1) drawn by the
  * host, weight_blob: sh_vae_blob_floats() floats packed as documented in csrc/pose_vae.cu.
- * loss3 = (loss, recon_mse, kld); grad_x [M,123]; scratch >= 16 bytes, 8-byte aligned. */
+ * loss3 = (loss, recon_mse, kld); grad_x [M,123]; scratch >= 16 bytes, 8-byte aligned.
+ * M_mean >= M: number of rows the reconstruction MSE is averaged over (= M on one GPU; = the GLOBAL batch rows when the
+ * batch is sharded over ranks, so that summing rank gradients reproduces the single-GPU gradient; the KLD is a sum). */
 size_t sh_vae_blob_floats(void);
-int sh_vae_prior_fwdbwd(const void* x, const void* eps, const void* weight_blob, int M, void* loss3, void* grad_x,
-                        void* scratch, void* stream);
+int sh_vae_prior_fwdbwd(const void* x, const void* eps, const void* weight_blob, int M, int M_mean, void* loss3,
+                        void* grad_x, void* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ heat-map heads
  * Replaces RecoverXYZCoordinateFromHeatmap.forward (network/util_modules.py:182-201), the uv/d channel split of
@@ -158,6 +161,28 @@ int sh_unpack_wgrad(const void* dw, int Cout, int Cin, int taps, int cout_ld, in
 /* torch.optim.Adam step with L2 weight decay on flat fp32 buffers (network/engine.py:95-97); grad is read as g*grad_scale. */
 int sh_adam_step(void* p, const void* g, void* m, void* v, long n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int step, float grad_scale, void* stream);
+/* Same update with the learning rate (fp32) and the step counter (int32, incremented by the call) in DEVICE memory,
+ * so that a captured CUDA graph of the whole train step can be replayed while the StepLR schedule
+ * (network/engine.py:98-99) moves the learning rate. */
+int sh_adam_step_dev(void* p, const void* g, void* m, void* v, long n, const void* lr_dev, void* step_dev, float beta1,
+                     float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ train-step glue
+ * Replaces the weighting / summation of MultiTaskLoss.forward (network/create_network_and_criterion.py:171-181,
+ * 183-263) and Engine.sum_loss_terms (network/engine.py:144-148) for one stack output.
+ * Rows n < Ns of xyz [Ns+M,J,3] are synthetic (target_xyz4 float4 [Ns,J]: 0.1*MSE on z), rows Ns.. are the M = B*V real
+ * views.  g_mvproj [M,J,3], g_pose3 [3,M,J,3], g_prior [M,J*3] and the loss vectors are the outputs of the entries above
+ * (any may be NULL = head disabled); sse2 from sh_softargmax_fwd.  weights8 (HOST pointer) = (synt_hm, synt_pt,
+ * mv_projection, mv_consistency, hm_mean, prior, collision, bone_length).  mean_scale multiplies the gradient of every
+ * batch-MEAN term (1/world_size under data parallelism; the batch-SUM terms, collision and the KLD, are not scaled).
+ * Out: gxyz [Ns+M,J,3] = d(total)/d(xyz) (overwritten); terms9 += (synt_uv, synt_d, mv_projection, mv_consistency,
+ * uv_hm_mean, pose_prior, collision, bone_length, total)  (accumulated across stacks: zero it once per step). */
+int sh_step_combine(const void* g_mvproj, const void* g_pose3, const void* g_prior, const void* xyz,
+                    const void* target_xyz4, const void* loss_mv3, const void* loss_pose3, const void* loss_prior3,
+                    const void* sse2, int Ns, int M, int J, int hw, const float* weights8, float mean_scale, void* gxyz,
+                    void* terms9, void* stream);
+/* y = x * s on n fp32 elements: real_dms * depth_scale (network/engine.py:337), xyz / 100 (create_network_and_criterion.py:240). */
+int sh_scale(const void* x, float s, long n, void* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -90,54 +90,77 @@ def det_state_dict(num_outputs=82, num_stacks=1, seed=7):
     return sd
 
 
-def _bottleneck(x, sd, p):
-    def gn(t, n, g=16):
-        return F.relu(F.group_norm(t, g, sd[p + n + '.weight'], sd[p + n + '.bias']))
+class _RoundBf16(torch.autograd.Function):
+    """Round-to-bf16 in the forward AND of the gradient in the backward: models a tensor materialised in bf16."""
 
-    def conv(t, n, pad=0):
-        return F.conv2d(t, sd[p + n + '.weight'], sd[p + n + '.bias'], padding=pad)
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def _ident(x):
+    return x
+
+
+def _bottleneck(x, sd, p, q=_ident):
+    def gn(t, n, g=16):
+        return q(F.relu(F.group_norm(t, g, sd[p + n + '.weight'], sd[p + n + '.bias'])))
+
+    def conv(t, n, pad=0, res=None):
+        y = F.conv2d(t, q(sd[p + n + '.weight']), sd[p + n + '.bias'], padding=pad)
+        return q(y if res is None else y + res)
 
     out = conv(gn(x, 'bn1'), 'conv1')
     out = conv(gn(out, 'bn2'), 'conv2', 1)
-    out = conv(gn(out, 'bn3'), 'conv3')
+    a3 = gn(out, 'bn3')
     res = conv(x, 'downsample.0') if (p + 'downsample.0.weight') in sd else x
-    return out + res
+    return conv(a3, 'conv3', res=res)
 
 
-def _hourglass(n, x, sd, p):
-    up1 = _bottleneck(x, sd, '%shg.%d.0.0.' % (p, n - 1))
-    low1 = _bottleneck(F.max_pool2d(x, 2, stride=2), sd, '%shg.%d.1.0.' % (p, n - 1))
+def _hourglass(n, x, sd, p, q=_ident):
+    up1 = _bottleneck(x, sd, '%shg.%d.0.0.' % (p, n - 1), q)
+    low1 = _bottleneck(F.max_pool2d(x, 2, stride=2), sd, '%shg.%d.1.0.' % (p, n - 1), q)
     if n > 1:
-        low2, latent = _hourglass(n - 1, low1, sd, p)
+        low2, latent = _hourglass(n - 1, low1, sd, p, q)
     else:
-        low2 = _bottleneck(low1, sd, '%shg.%d.3.0.' % (p, n - 1))
+        low2 = _bottleneck(low1, sd, '%shg.%d.3.0.' % (p, n - 1), q)
         latent = low2
-    low3 = _bottleneck(low2, sd, '%shg.%d.2.0.' % (p, n - 1))
+    low3 = _bottleneck(low2, sd, '%shg.%d.2.0.' % (p, n - 1), q)
     up2 = F.interpolate(low3, scale_factor=2, mode='bilinear', align_corners=False)
-    return up1 + up2, latent
+    return q(up1 + up2), latent
 
 
-def hourglass_forward(x, sd, num_stacks=1, prefix=''):
-    """x [N,S,S] or [N,1,S,S] -> (list of score [N,num_outputs,S/4,S/4], list of latent [N,256,S/16,S/16])."""
+def hourglass_forward(x, sd, num_stacks=1, prefix='', round_bf16=False):
+    """x [N,S,S] or [N,1,S,S] -> (list of score [N,num_outputs,S/4,S/4], list of latent [N,256,S/16,S/16]).
+
+    round_bf16=False is the reference (fp32 everywhere).  round_bf16=True evaluates the SAME graph in fp32 arithmetic
+    but rounds to bf16 every tensor (and its gradient) that the B200 implementation materialises in bf16 — conv
+    weights, conv outputs (after the fused residual add), GroupNorm+ReLU outputs, the up-sample sum — which is the
+    yardstick for "no worse than bf16 storage allows" in tests/test_gpu_nn.py."""
     p = prefix
+    q = _RoundBf16.apply if round_bf16 else _ident
     if x.dim() == 3:
         x = x[:, None]
-    x = F.conv2d(x, sd[p + 'conv1.weight'], sd[p + 'conv1.bias'], stride=2, padding=2)
-    x = F.relu(F.group_norm(x, 4, sd[p + 'bn1.weight'], sd[p + 'bn1.bias']))
-    x = _bottleneck(x, sd, p + 'layer1.0.')
+    x = q(F.conv2d(x, sd[p + 'conv1.weight'], sd[p + 'conv1.bias'], stride=2, padding=2))
+    x = q(F.relu(F.group_norm(x, 4, sd[p + 'bn1.weight'], sd[p + 'bn1.bias'])))
+    x = _bottleneck(x, sd, p + 'layer1.0.', q)
     x = F.max_pool2d(x, 2, stride=2)
-    x = _bottleneck(x, sd, p + 'layer2.0.')
-    x = _bottleneck(x, sd, p + 'layer3.0.')
+    x = _bottleneck(x, sd, p + 'layer2.0.', q)
+    x = _bottleneck(x, sd, p + 'layer3.0.', q)
     outs, latents = [], []
     for i in range(num_stacks):
-        y, latent = _hourglass(2, x, sd, '%shg.%d.' % (p, i))
-        y = _bottleneck(y, sd, '%sres.%d.0.' % (p, i))
-        y = F.conv2d(y, sd['%sfc.%d.0.weight' % (p, i)], sd['%sfc.%d.0.bias' % (p, i)])
-        y = F.relu(F.group_norm(y, 16, sd['%sfc.%d.1.weight' % (p, i)], sd['%sfc.%d.1.bias' % (p, i)]))
-        score = F.conv2d(y, sd['%sscore.%d.weight' % (p, i)], sd['%sscore.%d.bias' % (p, i)])
+        y, latent = _hourglass(2, x, sd, '%shg.%d.' % (p, i), q)
+        y = _bottleneck(y, sd, '%sres.%d.0.' % (p, i), q)
+        y = q(F.conv2d(y, q(sd['%sfc.%d.0.weight' % (p, i)]), sd['%sfc.%d.0.bias' % (p, i)]))
+        y = q(F.relu(F.group_norm(y, 16, sd['%sfc.%d.1.weight' % (p, i)], sd['%sfc.%d.1.bias' % (p, i)])))
+        score = F.conv2d(y, q(sd['%sscore.%d.weight' % (p, i)]), sd['%sscore.%d.bias' % (p, i)])
         outs.append(score)
         latents.append(latent)
         if i < num_stacks - 1:
-            x = x + F.conv2d(y, sd['%sfc_.%d.weight' % (p, i)], sd['%sfc_.%d.bias' % (p, i)]) \
-                  + F.conv2d(score, sd['%sscore_.%d.weight' % (p, i)], sd['%sscore_.%d.bias' % (p, i)])
+            t = q(x + F.conv2d(y, q(sd['%sfc_.%d.weight' % (p, i)]), sd['%sfc_.%d.bias' % (p, i)]))
+            x = q(t + F.conv2d(q(score), q(sd['%sscore_.%d.weight' % (p, i)]), sd['%sscore_.%d.bias' % (p, i)]))
     return outs, latents

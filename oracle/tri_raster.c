@@ -10,8 +10,9 @@
  * reciprocal of the 1/z blend (:109).  Min-combination is order independent, so a serial loop is exact.
  *
  * `use_fma` selects how a*b+c sub-expressions are rounded: 0 = every operation rounded separately
- * (ISO C), 1 = the fused multiply-adds that nvcc's default contraction (-fmad=true) emits for the
- * reference binary (checked against `cuobjdump -sass oracle/_ref/depth_rasterization_ref.so`).
+ * (ISO C), 1 = exactly the fused multiply-adds that nvcc 12.9's default contraction (-fmad=true) emitted for the
+ * reference binary (read off `cuobjdump -sass oracle/_ref/depth_rasterization_ref.so`; with it this oracle is
+ * bit-identical to the reference kernel run on the GPU box — tests/test_gpu_kernels.py checks all three ways).
  * Additionally records the winning face per pixel (the "integer z-buffer argmin index" of
  * BASELINE.json, which the reference itself never materialises).
  */
@@ -76,8 +77,13 @@ static void raster_one(const float *f, int width, int height, float *zbuf, int32
             const float yf = (float)yi;
             float w[3], wsum = 0;
             for (int k = 0; k < 3; k++) {
-                float v = use_fma ? fmaf(inv[3 * k], xf, inv[3 * k + 1] * yf) + inv[3 * k + 2]
-                                  : inv[3 * k] * xf + inv[3 * k + 1] * yf + inv[3 * k + 2];    /* .cu:99 */
+                float v;                                                                       /* .cu:99 */
+                if (!use_fma)
+                    v = inv[3 * k] * xf + inv[3 * k + 1] * yf + inv[3 * k + 2];
+                else if (k == 0) /* reference binary: row 0 fuses the x product ... */
+                    v = fmaf(inv[0], xf, inv[1] * yf) + inv[2];
+                else             /* ... rows 1, 2 the y product (their x products are hoisted out of the row loop) */
+                    v = fmaf(yf, inv[3 * k + 1], xf * inv[3 * k]) + inv[3 * k + 2];
                 v = (float)fmin(fmax((double)v, 0.), 1.);                                    /* .cu:103 */
                 w[k] = v;
                 wsum += v;

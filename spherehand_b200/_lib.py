@@ -14,7 +14,7 @@ HEADER_PATH = os.path.join(_ROOT, 'include', 'spherehand_b200.h')
 
 _CTYPES = {
     'void*': ctypes.c_void_p, 'const void*': ctypes.c_void_p, 'int': ctypes.c_int, 'float': ctypes.c_float,
-    'long': ctypes.c_long, 'size_t': ctypes.c_size_t, 'const char*': ctypes.c_char_p,
+    'long': ctypes.c_long, 'const float*': ctypes.c_void_p, 'size_t': ctypes.c_size_t, 'const char*': ctypes.c_char_p,
 }
 
 
@@ -27,7 +27,7 @@ def parse_header(path=HEADER_PATH):
     src = open(path).read()
     src = re.sub(r'/\*.*?\*/', ' ', src, flags=re.S)
     protos = {}
-    for m in re.finditer(r'(const char\*|int|size_t)\s+(sh_\w+)\s*\(([^)]*)\)\s*;', src):
+    for m in re.finditer(r'(const char\*|int|size_t|long)\s+(sh_\w+)\s*\(([^)]*)\)\s*;', src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         argtypes = []
         if args and args != 'void':

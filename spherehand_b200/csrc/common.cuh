@@ -16,6 +16,8 @@
 
 // Last error text (thread-unsafe by design: the reference path is single-threaded).
 extern char g_sh_last_error[512];
+// Number of kernel launches issued through this library (every launch site ends in SH_CHECK_LAUNCH).
+extern unsigned long long g_sh_launches;
 
 #define SH_REQUIRE(cond, ...)                                                   \
     do {                                                                        \
@@ -28,6 +30,7 @@ extern char g_sh_last_error[512];
 #define SH_CHECK_LAUNCH(name)                                                                       \
     do {                                                                                            \
         cudaError_t e__ = cudaGetLastError();                                                       \
+        ++g_sh_launches;                                                                            \
         if (e__ != cudaSuccess) {                                                                   \
             snprintf(g_sh_last_error, sizeof(g_sh_last_error), "%s: %s", name, cudaGetErrorString(e__)); \
             return SH_ERR_CUDA;                                                                     \

@@ -113,7 +113,7 @@ __device__ __forceinline__ void gn_relu_bwd(const float* __restrict__ gamma, con
 }
 
 __global__ void __launch_bounds__(kThreads) vae_prior_kernel(const float* __restrict__ x, const float* __restrict__ eps,
-                                                             const VaeWeights W, int M, double* __restrict__ acc,
+                                                             const VaeWeights W, int M, int M_mean, double* __restrict__ acc,
                                                              float* __restrict__ grad_x) {
     extern __shared__ float sm[];
     float* s_x = sm;                       // [RB][128]
@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(kThreads) vae_prior_kernel(const float* __rest
     gn_relu_fwd(W.g4, W.be4, s_a, s_h[3], s_xh[3], s_rs + 3 * RB * 16);
     dense_fwd(W.w5t, W.b5, HID, POSE, s_h[3], HID, s_rec, 128);
 
-    // ---------------- loss + seed gradient  (mean over M*123 elements)
-    const float n_inv = 1.f / ((float)M * POSE);
+    // ---------------- loss + seed gradient  (mean over M_mean*123 elements: M_mean = rows of the GLOBAL batch)
+    const float n_inv = 1.f / ((float)M_mean * POSE);
     float sse = 0.f;
     for (int i = t; i < RB * 128; i += kThreads) {
         const int r = i / 128, k = i % 128;
@@ -233,10 +233,10 @@ SH_EXPORT size_t sh_vae_blob_floats(void) {
     return n;
 }
 
-SH_EXPORT int sh_vae_prior_fwdbwd(const void* x, const void* eps, const void* weight_blob, int M, void* loss3,
+SH_EXPORT int sh_vae_prior_fwdbwd(const void* x, const void* eps, const void* weight_blob, int M, int M_mean, void* loss3,
                                    void* grad_x, void* scratch, void* stream) {
     SH_REQUIRE(x && eps && weight_blob && loss3 && grad_x && scratch, "sh_vae_prior_fwdbwd: null pointer");
-    SH_REQUIRE(M >= 1, "sh_vae_prior_fwdbwd: bad M");
+    SH_REQUIRE(M >= 1 && M_mean >= M, "sh_vae_prior_fwdbwd: bad M / M_mean");
     cudaStream_t st = (cudaStream_t)stream;
     const float* p = (const float*)weight_blob;
     VaeWeights W;
@@ -255,10 +255,10 @@ SH_EXPORT int sh_vae_prior_fwdbwd(const void* x, const void* eps, const void* we
         attr_set = true;
     }
     SH_CUDA(cudaMemsetAsync(scratch, 0, 16, st));
-    vae_prior_kernel<<<sh_div_up(M, RB), kThreads, smem, st>>>((const float*)x, (const float*)eps, W, M, (double*)scratch,
+    vae_prior_kernel<<<sh_div_up(M, RB), kThreads, smem, st>>>((const float*)x, (const float*)eps, W, M, M_mean, (double*)scratch,
                                                               (float*)grad_x);
     SH_CHECK_LAUNCH("vae_prior_kernel");
-    vae_finish_kernel<<<1, 32, 0, st>>>((const double*)scratch, M, (float*)loss3);
+    vae_finish_kernel<<<1, 32, 0, st>>>((const double*)scratch, M_mean, (float*)loss3);
     SH_CHECK_LAUNCH("vae_finish_kernel");
     return SH_OK;
 }

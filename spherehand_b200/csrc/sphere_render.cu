@@ -192,10 +192,10 @@ int pick_tiles_per_block(int n_tiles, int N) {
 
 SH_EXPORT int sh_sphere_render_fwd(const void* spheres, int N, int J, int H, int W, void* depth, void* idx,
                                     void* stream) {
-    SH_REQUIRE(spheres && depth && idx, "sh_sphere_render_fwd: null pointer");
     SH_REQUIRE(J >= 1 && J <= kMaxJ, "sh_sphere_render_fwd: J=%d outside [1,%d]", J, kMaxJ);
     SH_REQUIRE(N >= 0 && H >= 1 && W >= 1 && N <= 65535 * 64, "sh_sphere_render_fwd: bad N/H/W");
-    if (N == 0) return SH_OK;
+    if (N == 0) return SH_OK;   // empty batch: nothing to read or write (pointers may be null)
+    SH_REQUIRE(spheres && depth && idx, "sh_sphere_render_fwd: null pointer");
     SH_REQUIRE(((uintptr_t)spheres & 15) == 0, "sh_sphere_render_fwd: spheres must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int px = (W % 4 == 0 && ((uintptr_t)depth & 15) == 0 && ((uintptr_t)idx & 3) == 0) ? 4 : 1;
@@ -219,10 +219,10 @@ SH_EXPORT int sh_sphere_render_fwd(const void* spheres, int N, int J, int H, int
 
 SH_EXPORT int sh_sphere_render_bwd(const void* grad_depth, const void* idx, const void* spheres, int N, int J,
                                     int H, int W, void* grad_spheres, void* stream) {
-    SH_REQUIRE(grad_depth && idx && spheres && grad_spheres, "sh_sphere_render_bwd: null pointer");
     SH_REQUIRE(J >= 1 && J <= kMaxJ, "sh_sphere_render_bwd: J=%d outside [1,%d]", J, kMaxJ);
     SH_REQUIRE(N >= 0 && H >= 1 && W >= 1, "sh_sphere_render_bwd: bad N/H/W");
     if (N == 0) return SH_OK;
+    SH_REQUIRE(grad_depth && idx && spheres && grad_spheres, "sh_sphere_render_bwd: null pointer");
     SH_REQUIRE(((uintptr_t)spheres & 15) == 0, "sh_sphere_render_bwd: spheres must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     SH_CUDA(cudaMemsetAsync(grad_spheres, 0, (size_t)N * J * 16, st));

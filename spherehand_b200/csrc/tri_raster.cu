@@ -6,9 +6,9 @@
 // The reference launches <<<B*F, 1>>> (one thread per block, 1/32 lane utilisation) with a CAS-loop float
 // atomicMin.  Here 8 lanes share a triangle (4 triangles per warp, columns strided across the lanes), the
 // z-test is a single native integer atomic (sign-split ordering of IEEE floats) and the 1000.0 fill is one
-// vectorised pass.  The per-column / per-pixel expressions are written exactly as in the reference
-// (float storage, double-promoted max/min/ceil, truncating int conversion, 1./(...) in double) so that pixel
-// coverage — an integer decision — is taken on identical values.
+// vectorised pass.  The per-column / per-pixel arithmetic reproduces the reference's rounding sequence operation by
+// operation (float storage, double-promoted max/min/ceil, truncating int conversion, and the exact FMA fusions of
+// the reference binary) so that pixel coverage — an integer decision — and depth are bit-identical to it.
 //
 // A second entry rasterises only on the sample lattice the reference's 640->S bilinear resize actually
 // reads (S=128 -> pixel (5i+2,5j+2); S=64 -> {10i+4,10i+5}^2), which is exact, not an
@@ -49,19 +49,23 @@ __device__ __forceinline__ int lat_first(const Lattice& L, int x) {
     return q;
 }
 
-template <bool LATTICE>
-__global__ void __launch_bounds__(128) tri_raster_kernel(const int num_faces, const long total_faces, const int width,
-                                                         const int height, const float* __restrict__ face_vertices,
-                                                         float* __restrict__ depth_map, const Lattice L) {
-    const long gid = (long)blockIdx.x * (blockDim.x / kLanesPerTri) + threadIdx.x / kLanesPerTri;
-    const int sub = threadIdx.x % kLanesPerTri;
-    if (gid >= total_faces) return;
-    const long image = gid / num_faces;
-    const float* f = &face_vertices[gid * 9];
+// Per-triangle constants.  Every floating-point operation below is an explicit round-to-nearest intrinsic in the
+// exact sequence (which products are fused into an FMA, which are rounded first) that the reference binary executes
+// — read off `cuobjdump -sass` of the reference kernel built by oracle/build_ref.py (nvcc 12.9, default -fmad=true) —
+// so coverage AND depth are bit-identical to it, for the full-image and the lattice variant alike, whatever this
+// translation unit's own contraction choices would have been.
+struct TriSetup {
+    float ax, ay, bx, by, cx;
+    float az, bz, cz;
+    float e[9];                 // rows of the inverse edge-function matrix (.cu:57-65)
+    float s_lo, s_hi, s_long;   // slopes of edges lo-mid, mid-hi, lo-hi
+    bool lo_vertical, hi_vertical;
+};
 
+__device__ __forceinline__ bool tri_setup(const float* __restrict__ f, TriSetup& t) {
     // back-face cull on the raw winding (.cu:33)
-    if ((f[7] - f[1]) * (f[3] - f[0]) < (f[4] - f[1]) * (f[6] - f[0])) return;
-
+    if (__fmul_rn(__fsub_rn(f[7], f[1]), __fsub_rn(f[3], f[0])) < __fmul_rn(__fsub_rn(f[4], f[1]), __fsub_rn(f[6], f[0])))
+        return false;
     // vertex order by x: lo / mid / hi, ties resolved as the reference does (.cu:36-45)
     int lo, hi;
     if (f[0] < f[3]) {
@@ -72,63 +76,90 @@ __global__ void __launch_bounds__(128) tri_raster_kernel(const int num_faces, co
         hi = (f[0] < f[6]) ? 2 : 0;
     }
     const int mid = 3 - lo - hi;
-    const float ax = f[3 * lo], ay = f[3 * lo + 1], az = f[3 * lo + 2];
-    const float bx = f[3 * mid], by = f[3 * mid + 1], bz = f[3 * mid + 2];
-    const float cx = f[3 * hi], cy = f[3 * hi + 1], cz = f[3 * hi + 2];
-    if (ax == cx) return;   // zero width (.cu:54)
+    const float ax = f[3 * lo], ay = f[3 * lo + 1];
+    const float bx = f[3 * mid], by = f[3 * mid + 1];
+    const float cx = f[3 * hi], cy = f[3 * hi + 1];
+    if (ax == cx) return false;   // zero width (.cu:54)
+    t.ax = ax; t.ay = ay; t.bx = bx; t.by = by; t.cx = cx;
+    t.az = f[3 * lo + 2]; t.bz = f[3 * mid + 2]; t.cz = f[3 * hi + 2];
+    const float by_cy = __fsub_rn(by, cy), cy_ay = __fsub_rn(cy, ay), ay_by = __fsub_rn(ay, by);
+    const float cx_bx = __fsub_rn(cx, bx), ax_cx = __fsub_rn(ax, cx), bx_ax = __fsub_rn(bx, ax);
+    // den = cx(ay-by) + ax(by-cy) + bx(cy-ay): middle product rounded, the outer two fused (.cu:61-64)
+    const float den = __fmaf_rn(bx, cy_ay, __fmaf_rn(cx, ay_by, __fmul_rn(ax, by_cy)));
+    t.e[0] = __fdiv_rn(by_cy, den);
+    t.e[1] = __fdiv_rn(cx_bx, den);
+    t.e[2] = __fdiv_rn(__fmaf_rn(bx, cy, -__fmul_rn(cx, by)), den);
+    t.e[3] = __fdiv_rn(cy_ay, den);
+    t.e[4] = __fdiv_rn(ax_cx, den);
+    t.e[5] = __fdiv_rn(__fmaf_rn(cx, ay, -__fmul_rn(ax, cy)), den);
+    t.e[6] = __fdiv_rn(ay_by, den);
+    t.e[7] = __fdiv_rn(bx_ax, den);
+    t.e[8] = __fdiv_rn(__fmaf_rn(ax, by, -__fmul_rn(bx, ay)), den);
+    t.lo_vertical = !(bx_ax != 0.f);
+    t.hi_vertical = !(cx_bx != 0.f);
+    t.s_lo = __fdiv_rn(__fsub_rn(by, ay), bx_ax);
+    t.s_hi = __fdiv_rn(__fsub_rn(cy, by), cx_bx);
+    t.s_long = __fdiv_rn(cy_ay, __fsub_rn(cx, ax));
+    return true;
+}
 
-    // rows of the inverse edge-function matrix (.cu:57-65); expression shapes kept so nvcc contracts the same FMAs
-    float e[9] = {by - cy, cx - bx, bx * cy - cx * by,
-                  cy - ay, ax - cx, cx * ay - ax * cy,
-                  ay - by, bx - ax, ax * by - bx * ay};
-    float e_den = (cx * (ay - by) + ax * (by - cy) + bx * (cy - ay));
-#pragma unroll
-    for (int k = 0; k < 9; k++) e[k] /= e_den;
+// Row span [yi_min, yi_max] of column xi (.cu:72-90): bounds are taken in double and truncated, as the reference does.
+__device__ __forceinline__ void tri_column_span(const TriSetup& t, int32_t xi, int height, int32_t& yi_min, int32_t& yi_max) {
+    const float xf = (float)xi;
+    float y_edge;
+    if (xf <= t.bx)
+        y_edge = t.lo_vertical ? t.by : __fmaf_rn(__fsub_rn(xf, t.ax), t.s_lo, t.ay);
+    else
+        y_edge = t.hi_vertical ? t.by : __fmaf_rn(__fsub_rn(xf, t.bx), t.s_hi, t.by);
+    const float y_long = __fmaf_rn(__fsub_rn(xf, t.ax), t.s_long, t.ay);
+    yi_min = max(0., ceil(min(y_edge, y_long)));
+    yi_max = min(max(y_edge, y_long), height - 1.);
+}
 
-    const int32_t xi_min = max(ceil(ax), 0.);          // float -> double -> truncate (.cu:68)
-    const int32_t xi_max = min(cx, width - 1.);        // (.cu:69)
+// Depth of the triangle's plane at pixel (xi, yi): clamped + renormalised barycentrics, 1/z blend (.cu:97-109).
+__device__ __forceinline__ float tri_pixel_depth(const TriSetup& t, int32_t xi, int32_t yi) {
+    const float xf = (float)xi, yf = (float)yi;
+    // the reference binary fuses row 0 on the x product and rows 1, 2 on the y product (its x products are hoisted)
+    float w0 = __fadd_rn(__fmaf_rn(t.e[0], xf, __fmul_rn(t.e[1], yf)), t.e[2]);
+    float w1 = __fadd_rn(__fmaf_rn(yf, t.e[4], __fmul_rn(xf, t.e[3])), t.e[5]);
+    float w2 = __fadd_rn(__fmaf_rn(yf, t.e[7], __fmul_rn(xf, t.e[6])), t.e[8]);
+    w0 = min(max(w0, 0.), 1.);
+    w1 = min(max(w1, 0.), 1.);
+    w2 = min(max(w2, 0.), 1.);
+    const float total = __fadd_rn(__fadd_rn(__fadd_rn(0.f, w0), w1), w2);
+    w0 = __fdiv_rn(w0, total);
+    w1 = __fdiv_rn(w1, total);
+    w2 = __fdiv_rn(w2, total);
+    const float q = __fadd_rn(__fadd_rn(__fdiv_rn(w0, t.az), __fdiv_rn(w1, t.bz)), __fdiv_rn(w2, t.cz));
+    return __frcp_rn(q);   // == (float)(1. / (double)q): the double quotient rounds to the correctly rounded float
+}
+
+template <bool LATTICE>
+__global__ void __launch_bounds__(128) tri_raster_kernel(const int num_faces, const long total_faces, const int width,
+                                                         const int height, const float* __restrict__ face_vertices,
+                                                         float* __restrict__ depth_map, const Lattice L) {
+    const long gid = (long)blockIdx.x * (blockDim.x / kLanesPerTri) + threadIdx.x / kLanesPerTri;
+    const int sub = threadIdx.x % kLanesPerTri;
+    if (gid >= total_faces) return;
+    const long image = gid / num_faces;
+    TriSetup t;
+    if (!tri_setup(&face_vertices[gid * 9], t)) return;
+
+    const int32_t xi_min = max(ceil(t.ax), 0.);        // float -> double -> truncate (.cu:68)
+    const int32_t xi_max = min(t.cx, width - 1.);      // (.cu:69)
     float* out = depth_map + image * (LATTICE ? (long)L.ow * L.oh : (long)width * height);
 
-    int q = LATTICE ? lat_first(L, xi_min) + sub : xi_min + sub;
-    for (;; q += kLanesPerTri) {
+    // the 8 lanes of a triangle take columns round-robin
+    for (int q = (LATTICE ? lat_first(L, xi_min) : xi_min) + sub;; q += kLanesPerTri) {
         const int32_t xi = LATTICE ? lat_coord(L, q) : q;
         if (xi > xi_max) break;
-        float y_edge, y_long;
-        if (xi <= bx) {                                 // left part: edge lo-mid (.cu:73-79)
-            if (bx - ax != 0) {
-                y_edge = (by - ay) / (bx - ax) * (xi - ax) + ay;
-            } else {
-                y_edge = by;
-            }
-        } else {                                        // right part: edge mid-hi (.cu:80-86)
-            if (cx - bx != 0) {
-                y_edge = (cy - by) / (cx - bx) * (xi - bx) + by;
-            } else {
-                y_edge = by;
-            }
-        }
-        y_long = (cy - ay) / (cx - ax) * (xi - ax) + ay; // long edge lo-hi (.cu:87)
-
-        const int32_t yi_min = max(0., ceil(min(y_edge, y_long)));   // (.cu:89)
-        const int32_t yi_max = min(max(y_edge, y_long), height - 1.); // (.cu:90)
-        int r = LATTICE ? lat_first(L, yi_min) : yi_min;
-        for (;; ++r) {
+        int32_t yi_min, yi_max;
+        tri_column_span(t, xi, height, yi_min, yi_max);
+        for (int r = LATTICE ? lat_first(L, yi_min) : yi_min;; ++r) {
             const int32_t yi = LATTICE ? lat_coord(L, r) : r;
             if (yi > yi_max) break;
-            float bary[3];
-#pragma unroll
-            for (int k = 0; k < 3; k++) bary[k] = e[3 * k + 0] * xi + e[3 * k + 1] * yi + e[3 * k + 2];
-            float total = 0;
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                bary[k] = min(max(bary[k], 0.), 1.);    // clamp in double, store float (.cu:103)
-                total += bary[k];
-            }
-#pragma unroll
-            for (int k = 0; k < 3; k++) bary[k] /= total;
-            const float zp = 1. / (bary[0] / az + bary[1] / bz + bary[2] / cz);   // perspective-style 1/z blend (.cu:109)
-            const long index = LATTICE ? (long)r * L.ow + q : (long)yi * width + xi;
-            atomic_min_float(&out[index], zp);
+            const float zp = tri_pixel_depth(t, xi, yi);
+            atomic_min_float(&out[LATTICE ? (long)r * L.ow + q : (long)yi * width + xi], zp);
         }
     }
 }

@@ -1,0 +1,211 @@
+"""The self-supervised train step on the B200 kernels: body of `Engine._epoch_with_both`
+(/root/reference/network/engine.py:349-376) — synthetic branch -> zero_grad -> network -> losses -> sum -> backward ->
+Adam step — issued as one static sequence of C-ABI kernel launches and replayed as a CUDA graph.
+
+    synthetic branch (no grad)   HandSynthesizer.forward            network/util_modules.py:104-122
+    network                      HeatmapEstimationNetwork.forward   network/create_network_and_criterion.py:84-144
+    losses                       MultiTaskLoss.forward              network/create_network_and_criterion.py:183-263
+    optimiser                    Adam(lr, weight_decay=1e-5)        network/engine.py:95-97
+
+torch is used for device memory, streams, RNG draws (same draws, same order as the reference: SURVEY §7.3-9), CUDA-graph
+capture and the NCCL gradient all-reduce; every arithmetic kernel is in libspherehand_b200.so.  There is no CPU path.
+
+Data parallelism: tuples and synthetic poses shard across ranks; one all-reduce(SUM) of the flat fp32
+gradient per step.  Batch-MEAN loss terms are pre-scaled by 1/world_size and batch-SUM terms (collision, VAE KLD) are
+not, so the summed gradient equals the single-GPU gradient at the global batch.
+"""
+import torch
+
+from . import _lib, ops
+from .network.hourglass import HourglassNet
+
+LOSS_WEIGHTS = {          # MultiTaskLoss.weights, create_network_and_criterion.py:171-181
+    'synt_hm': 1e3, 'synt_pt': 1e-1, 'mv_consistency': 1e-3, 'mv_projection': 1.0, 'temporal_smooth': 1.0,
+    'prior': 1e-2, 'hm_mean': 1e-2, 'domain': 0.0, 'collision': 1.0, 'bone_length': 1.0,
+}
+TERM_NAMES = ('synt_uv', 'synt_d', 'mv_projection', 'mv_consistency', 'uv_hm_mean', 'pose_prior', 'collision',
+              'bone_length', 'total')
+
+_LATTICE = {128: (5, 2, 1), 64: (10, 4, 2)}      # 640 -> S bilinear resize == these source samples
+
+
+class SelfSupTrainStep:
+    """One replica of the train step for B multi-view tuples x V views + Ns synthetic poses at S x S depth maps."""
+
+    def __init__(self, net, hand, vae_blob, B, V, Ns, S, depth_scale=0.01, lr=1e-4, weight_decay=1e-5,
+                 weights=None, use_prior=True, use_collision=True, use_bone_length=True, use_mv_projection=True,
+                 use_mv_consistency=True, world_size=1, process_group=None, use_graph=True):
+        if not isinstance(net, HourglassNet):
+            raise TypeError('net must be a spherehand_b200 HourglassNet')
+        if S not in _LATTICE:
+            raise ValueError('depth size must be 64 or 128 (the 640 -> S resize lattice is tabulated for those)')
+        dev = next(net.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('SelfSupTrainStep needs a CUDA (sm_100a) device; there is no CPU fallback')
+        self.net, self.hand, self.vae_blob, self.dev = net, hand, vae_blob, dev
+        self.B, self.V, self.Ns, self.S, self.J = B, V, Ns, S, hand.num_keypoints
+        self.hm = S // 4
+        self.N = Ns + B * V
+        self.depth_scale = depth_scale
+        self.weights = dict(LOSS_WEIGHTS)
+        self.weights.update(weights or {})
+        self.flags = dict(prior=use_prior and vae_blob is not None, collision=use_collision, bone=use_bone_length,
+                          proj=use_mv_projection, cons=use_mv_consistency)
+        self.world_size, self.pg = world_size, process_group
+        self.use_graph = use_graph
+        self.betas, self.eps_adam, self.weight_decay = (0.9, 0.999), 1e-8, weight_decay
+        f32 = dict(device=dev, dtype=torch.float32)
+        # ---- static input buffers (H2D targets)
+        self.real = torch.full((B, V, S, S), 100.0, **f32)             # mm, background 100.0
+        self.cams = torch.eye(4, **f32).repeat(B, V, 1, 1).contiguous()
+        self.inv_cams = self.cams.clone()
+        self.poses = torch.zeros((Ns, 26), **f32)
+        # ---- static RNG buffers (drawn on the host side of the graph, every step)
+        self.scales = torch.full((Ns, 3), 0.9, **f32)
+        self.rand_f = torch.ones((Ns,), **f32)
+        self.noise = torch.zeros((3, Ns, S, S), **f32)
+        self.vae_eps = torch.zeros((net.num_stacks, B * V, 32), **f32)
+        # ---- state
+        self.images = torch.zeros((self.N, S, S), **f32)
+        self.terms = torch.zeros(9, **f32)
+        net.flatten_parameters()
+        self.adam_m = torch.zeros_like(net._flat)
+        self.adam_v = torch.zeros_like(net._flat)
+        self.lr_dev = torch.tensor([lr], **f32)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.projected_dms = None
+        self._graphs = {}
+        self.launches_per_step = None
+
+    # ------------------------------------------------------------------ host-side plumbing
+    def set_lr(self, lr):
+        self.lr_dev.fill_(lr)
+
+    def load_batch(self, real_dms, camera_poses, inv_camera_poses, pose_parameters, non_blocking=True):
+        """Host (pinned) or device tensors -> the static device buffers."""
+        self.real.copy_(real_dms, non_blocking=non_blocking)
+        self.cams.copy_(camera_poses, non_blocking=non_blocking)
+        self.inv_cams.copy_(inv_camera_poses, non_blocking=non_blocking)
+        self.poses.copy_(pose_parameters, non_blocking=non_blocking)
+        return real_dms.numel() * 4 + 2 * camera_poses.numel() * 4 + pose_parameters.numel() * 4
+
+    def draw_randoms(self, generator=None):
+        """The step's random draws, in the reference's order: RandScale x,y,z (pointTransformation.py:140-142),
+        rand_f_ratio (util_modules.py:107), DepthNoise shift_x, shift_y, z (util_modules.py:64,69,83), VAE eps per stack
+        (pose_vae.py:51)."""
+        g = generator
+        self.scales.uniform_(0.85, 0.95, generator=g)
+        self.rand_f.uniform_(0.9, 1.1, generator=g)
+        self.noise.normal_(generator=g)
+        self.vae_eps.normal_(generator=g)
+
+    # ------------------------------------------------------------------ the step
+    def _forward_backward(self, is_mv):
+        net, hand = self.net, self.hand
+        B, V, Ns, S, J, hm, N = self.B, self.V, self.Ns, self.S, self.J, self.hm, self.N
+        M = B * V
+        w = self.weights
+        ms = 1.0 / self.world_size
+        # ---- synthetic branch (HandSynthesizer.forward): FK -> scale -> LBS -> project -> rasterise -> resize -> noise
+        step, off, noff = _LATTICE[S]
+        mats = ops.fk_fwd(self.poses, hand.offset_mats, hand.inv_offset_mats, self.scales)
+        pts = ops.lbs_fwd(mats, *hand.mesh_csr, right_hand=True, mode=1, cam=(320.0, 320.0, 640 / 300, 640 / 300),
+                          rand_f=self.rand_f)
+        fv = ops.gather_faces(pts, hand.faces)
+        z = ops.tri_raster_lattice_fwd(fv, 640, step, off, noff)
+        dm = ops.lattice_to_depth(z, S, noff, self.depth_scale)
+        ops.depth_noise(dm, self.noise[0], self.noise[1], self.noise[2], out=self.images[:Ns])
+        uvd = ops.lbs_fwd(mats, *hand.kp_csr, right_hand=True, mode=1, cam=(hm / 2, hm / 2, hm / 300, hm / 300),
+                          rand_f=self.rand_f)
+        uv_t, _d_t, xyz_t = ops.heatmap_render(uvd, hm)
+        # ---- real branch input: real_dms * depth_scale (engine.py:337)
+        ops.scale(self.real, self.depth_scale, self.images[Ns:])
+        # ---- network
+        scores, _latents = net.run_forward(self.images)
+        # ---- heads, per stack output
+        self.terms.zero_()
+        w8 = (w['synt_hm'], w['synt_pt'], w['mv_projection'], w['mv_consistency'] if is_mv else 0.0, w['hm_mean'],
+              w['prior'], w['collision'], w['bone_length'])
+        hw = hm * hm
+        gscores, projected = [], []
+        for si, score in enumerate(scores):
+            xyz, sse = ops.softargmax_fwd(score, J, Ns, uv_t, 1.0 / self.depth_scale, want_sse=True)
+            joints = xyz[Ns:].view(B, V, J, 3)
+            loss_mv = g_mv = loss_p = g_p = loss_v = g_v = None
+            if self.flags['proj']:
+                loss_mv, proj, g_mv = ops.mvproj_loss_fwdbwd(self.cams, self.inv_cams, joints, self.real, hand.radii, is_mv)
+                projected.append(proj)
+            pf = (1 if self.flags['cons'] else 0) | (2 if self.flags['collision'] else 0) | (4 if self.flags['bone'] else 0)
+            if pf:
+                loss_p, g_p = ops.pose_losses_fwdbwd(self.cams, joints, flags=pf)
+            if self.flags['prior']:
+                x = torch.empty((M, J * 3), device=self.dev, dtype=torch.float32)
+                ops.scale(xyz[Ns:], 0.01, x)
+                loss_v, g_v = ops.vae_prior_fwdbwd(x, self.vae_eps[si], self.vae_blob, M_mean=M * self.world_size)
+            gxyz = torch.empty_like(xyz)
+            ops.step_combine(xyz, Ns, M, J, hw, w8, gxyz, self.terms, g_mvproj=g_mv, g_pose3=g_p, g_prior=g_v,
+                             target_xyz4=xyz_t, loss_mv3=loss_mv, loss_pose3=loss_p, loss_prior3=loss_v, sse2=sse,
+                             mean_scale=ms)
+            gscore = torch.empty_like(score)
+            if score.shape[1] != 2 * J:
+                gscore.zero_()
+            ops.softargmax_bwd(score, gxyz, J, Ns, uv_t, 1.0 / self.depth_scale,
+                               c_synt=2.0 * w['synt_hm'] * ms / (Ns * J * hw) if Ns else 0.0,
+                               c_real=2.0 * w['hm_mean'] * ms / (M * J * hw) if M else 0.0, out=gscore)
+            gscores.append(gscore)
+        self.projected_dms = projected
+        net.run_backward(gscores)
+
+    def _optimizer(self):
+        net = self.net
+        ops.adam_step_dev(net._flat, net._flat_grad, self.adam_m, self.adam_v, self.lr_dev, self.step_dev,
+                          self.betas[0], self.betas[1], self.eps_adam, self.weight_decay)
+
+    def _allreduce(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.net._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _capture(self, is_mv):
+        """Warm up eagerly on a side stream (lazy CUDA init, cudaFuncSetAttribute, allocator), then capture."""
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        step0 = self.step_dev.clone()
+        flat0, m0, v0 = self.net._flat.clone(), self.adam_m.clone(), self.adam_v.clone()
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._forward_backward(is_mv)
+                self._optimizer()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        # the warm-up steps must not count as training
+        self.net._flat.copy_(flat0); self.adam_m.copy_(m0); self.adam_v.copy_(v0); self.step_dev.copy_(step0)
+        g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        n0 = _lib.lib().sh_launch_count()
+        with torch.cuda.graph(g_fb):
+            self._forward_backward(is_mv)
+        with torch.cuda.graph(g_opt, pool=g_fb.pool()):
+            self._optimizer()
+        self.launches_per_step = _lib.lib().sh_launch_count() - n0     # kernels of this library inside one step
+        return g_fb, g_opt
+
+    def step(self, is_mv=True):
+        """One optimisation step on the buffers filled by load_batch / draw_randoms.  Returns the device tensor of the
+        9 weighted loss terms (TERM_NAMES); reading it synchronises."""
+        if not self.use_graph:
+            self._forward_backward(is_mv)
+            self._allreduce()
+            self._optimizer()
+            return self.terms
+        key = bool(is_mv)
+        if key not in self._graphs:
+            self._graphs[key] = self._capture(is_mv)
+        g_fb, g_opt = self._graphs[key]
+        g_fb.replay()
+        self._allreduce()
+        g_opt.replay()
+        return self.terms
+
+    def loss_dict(self):
+        t = self.terms.tolist()
+        return dict(zip(TERM_NAMES, t))

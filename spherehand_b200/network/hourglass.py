@@ -375,6 +375,7 @@ class _Run:
                     ops.add(dscore, dsp, N, hh * hh, 128, tmp)
                     dscore = tmp
                     dyf = fcu_b(dx_next, 256)
+                self._tmp128().zero_()
                 ops.colsum(dscore, N, hh * hh, 128, self._tmp128())
                 net.grad_view(net.score[i].bias).copy_(self._tmp128()[:K])
                 dyf = sc_b(dscore, 128, dx_addend=dyf)

@@ -117,14 +117,14 @@ def vae_blob_from_state_dict(sd, device):
     return blob.to(device)
 
 
-def vae_prior_fwdbwd(x, eps, blob):
+def vae_prior_fwdbwd(x, eps, blob, M_mean=None):
     M = x.shape[0]
     dev = x.device
     loss3 = torch.empty(3, device=dev, dtype=torch.float32)
     grad = torch.empty((M, 123), device=dev, dtype=torch.float32)
     scratch = torch.empty(4, device=dev, dtype=torch.float64)
     _call('sh_vae_prior_fwdbwd', _chk(x, name='x'), _chk(eps, name='eps'), _chk(blob, name='weights'), M,
-          loss3.data_ptr(), grad.data_ptr(), scratch.data_ptr(), _stream())
+          M if M_mean is None else M_mean, loss3.data_ptr(), grad.data_ptr(), scratch.data_ptr(), _stream())
     return loss3, grad
 
 
@@ -182,11 +182,11 @@ def lattice_to_depth(z, S, noff, depth_scale):
     return dm
 
 
-def depth_noise(dm, nx, ny, nz, sx=0.5, sy=0.5, sz=0.05):
+def depth_noise(dm, nx, ny, nz, sx=0.5, sy=0.5, sz=0.05, out=None):
     B, H, W = dm.shape
-    out = torch.empty_like(dm)
+    out = torch.empty_like(dm) if out is None else out
     _call('sh_depth_noise', _chk(dm, name='dm'), _chk(nx, name='nx'), _chk(ny, name='ny'), _chk(nz, name='nz'), B, H, W,
-          sx, sy, sz, out.data_ptr(), _stream())
+          sx, sy, sz, _chk(out, name='out'), _stream())
     return out
 
 
@@ -283,3 +283,27 @@ def unpack_wgrad(dw, Cout, Cin, taps, cout_ld, cin_ld, grad):
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     _call('sh_adam_step', _chk(p, name='p'), _chk(g, name='g'), _chk(m, name='m'), _chk(v, name='v'), p.numel(), lr, beta1,
           beta2, eps, weight_decay, step, grad_scale, _stream())
+
+
+def adam_step_dev(p, g, m, v, lr_dev, step_dev, beta1, beta2, eps, weight_decay, grad_scale=1.0):
+    _call('sh_adam_step_dev', _chk(p, name='p'), _chk(g, name='g'), _chk(m, name='m'), _chk(v, name='v'), p.numel(),
+          _chk(lr_dev, name='lr'), _chk(step_dev, torch.int32, 'step'), beta1, beta2, eps, weight_decay, grad_scale, _stream())
+
+
+# ------------------------------------------------------------------------------------------------ train-step glue
+import ctypes as _ct
+
+
+def step_combine(xyz, Ns, M, J, hw, weights8, gxyz, terms9, g_mvproj=None, g_pose3=None, g_prior=None, target_xyz4=None,
+                 loss_mv3=None, loss_pose3=None, loss_prior3=None, sse2=None, mean_scale=1.0):
+    w = (_ct.c_float * 8)(*[float(x) for x in weights8])
+    _call('sh_step_combine', _opt(g_mvproj, name='g_mvproj'), _opt(g_pose3, name='g_pose3'), _opt(g_prior, name='g_prior'),
+          _chk(xyz, name='xyz'), _opt(target_xyz4, name='target_xyz4'), _opt(loss_mv3, name='loss_mv3'),
+          _opt(loss_pose3, name='loss_pose3'), _opt(loss_prior3, name='loss_prior3'), _opt(sse2, torch.float64, 'sse2'),
+          Ns, M, J, hw, _ct.cast(w, _ct.c_void_p), float(mean_scale), _chk(gxyz, name='gxyz'), _chk(terms9, name='terms9'),
+          _stream())
+
+
+def scale(x, s, out):
+    _call('sh_scale', _chk(x, name='x'), float(s), x.numel(), _chk(out, name='out'), _stream())
+    return out

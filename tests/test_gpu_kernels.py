@@ -251,33 +251,31 @@ def _face_verts(hand_model, n=3):
     return ops.gather_faces(pts, m.faces)
 
 
+def _same_bits(a, b):
+    return (a == b) | (np.isnan(a) & np.isnan(b))
+
+
 def test_tri_raster_vs_oracle_and_reference_kernel(hand_model):
+    """R1: CUDA kernel == C oracle (reference binary's rounding sequence) == the reference's own kernel, bit for bit."""
     fv = _face_verts(hand_model, 3)
     z = ops.tri_raster_fwd(fv, 640, 640).cpu().numpy()
     fvn = fv.cpu().numpy()
-    stats = {}
-    for fma in (False, True):
-        zo = synth.tri_raster(fvn, 640, 640, fma=fma)
-        cov_mis = int(((z < 1000) != (zo < 1000)).sum())
-        both = (z < 1000) & (zo < 1000)
-        with np.errstate(invalid='ignore', divide='ignore'):
-            bad = np.abs(z[both] - zo[both]) > 1e-4 * np.maximum(np.abs(zo[both]), 1.0)
-        stats[fma] = (cov_mis, int(bad.sum()), int(both.sum()))
-    print('tri_raster vs C oracle (cov mismatches, depth mismatches, covered): no-fma %s  fma %s' % (stats[False], stats[True]))
-    best = min(stats.values())
-    assert best[0] <= 2e-5 * 3 * 640 * 640          # coverage: knife-edge pixels only
-    assert best[1] <= 1e-3 * best[2]                 # depth: the 1/z blend near z=0 amplifies rounding
+    zo = synth.tri_raster(fvn, 640, 640, fma=True)
+    assert int(((z < 1000) != (zo < 1000)).sum()) == 0           # coverage: integer decision, bit-exact
+    assert _same_bits(z, zo).all()                               # depth: bit-exact
+    # the ISO-C rounding of the same algorithm (no FMA) differs only on knife-edge pixels / near-zero 1/z blends
+    zn = synth.tri_raster(fvn, 640, 640, fma=False)
+    both = (z < 1000) & (zn < 1000)
+    assert int(((z < 1000) != (zn < 1000)).sum()) <= 2e-5 * z.size
+    with np.errstate(invalid='ignore', divide='ignore'):
+        assert (np.abs(z[both] - zn[both]) > 1e-4 * np.maximum(np.abs(zn[both]), 1.0)).mean() < 0.05
     ref = _ref_kernel()
     if ref is None:
         pytest.skip('oracle/_ref/depth_rasterization_ref.so not built (build container only)')
     zr = ref.forward(640, 640, fv).cpu().numpy()
-    cov_mis = int(((z < 1000) != (zr < 1000)).sum())
-    same = (z == zr) | (np.isnan(z) & np.isnan(zr))
-    print('tri_raster vs REFERENCE kernel: coverage mismatches %d, value mismatches %d of %d' %
-          (cov_mis, int((~same).sum()), z.size))
-    assert cov_mis == 0                              # integer coverage decision: bit-exact
-    both = (z < 1000)
-    assert (np.abs(z[both] - zr[both]) <= 1e-4 * np.maximum(np.abs(zr[both]), 1e-3)).mean() > 0.9999
+    same = _same_bits(z, zr)
+    print('tri_raster vs REFERENCE kernel: value mismatches %d of %d' % (int((~same).sum()), z.size))
+    assert same.all()
 
 
 def test_tri_raster_lattice_equals_resized_full(hand_model):
@@ -287,7 +285,7 @@ def test_tri_raster_lattice_equals_resized_full(hand_model):
         lat = ops.tri_raster_lattice_fwd(fv, 640, step, off, noff)
         dm = ops.lattice_to_depth(lat, S, noff, 0.01)
         ref = torch.nn.functional.interpolate(full[:, None], size=(S, S), mode='bilinear', align_corners=False)[:, 0] * 0.01
-        assert (dm - ref).abs().max().item() < 1e-6
+        assert (dm - ref).abs().max().item() == 0.0      # the lattice is exact, not an approximation
     # drop-in entry semantics: untouched pixels are exactly 1000.0, empty face list is legal
     z = ops.tri_raster_fwd(torch.zeros((2, 0, 3, 3), device=DEV), 32, 16)
     assert z.shape == (2, 16, 32) and (z == 1000).all()

@@ -200,19 +200,44 @@ def test_hourglass_golden(stacks):
         errs.append(rel_err(lats[i].cpu(), g['latent%d' % i]))
     print('hourglass %d-stack forward rel errs (score, latent per stack):' % stacks, ['%.4f' % e for e in errs])
     assert max(errs) < 2e-2
-    gs = [torch.from_numpy(det_uniform(o.numel(), 100 + i).reshape(o.shape)).to(DEV) for i, o in enumerate(outs)]
-    sum((o * gg).sum() for o, gg in zip(outs, gs)).backward()
-    params = dict(net.named_parameters())
-    worst = {}
-    for k in g:
-        if k.startswith('grad.'):
-            worst[k[5:]] = rel_err(params[k[5:]].grad.cpu(), g[k])
-    norm_err = {}
-    for k in g:
-        if k.startswith('gradnorm.'):
-            norm_err[k[9:]] = abs(float(params[k[9:]].grad.double().norm()) / float(g[k]) - 1)
-    bad = sorted(norm_err.items(), key=lambda kv: -kv[1])[:5]
-    print('hourglass %d-stack grad rel errs:' % stacks, {k: '%.4f' % v for k, v in worst.items()})
-    print('worst grad-norm deviations:', bad)
-    assert max(worst.values()) < 5e-2
-    assert max(norm_err.values()) < 5e-2
+    # ---- gradients.  A deep bf16 network has inherent rounding noise in its gradients (tools/diag_hourglass.py), so the
+    # yardstick is torch evaluating the SAME graph in fp32 arithmetic with bf16 rounding at the same materialisation
+    # points (oracle.hourglass round_bf16=True): our error against the fp32 reference must not exceed that
+    # emulation's error (x1.5 + 2e-2 slack: both are noise realisations), parameter by parameter, for a white-noise upstream gradient (the golden
+    # fixture's) and for the MSE heat-map loss the reference trains with.
+    from oracle.hourglass import hourglass_forward
+    sd0 = {k: v.to(DEV) for k, v in det_state_dict(82, stacks, seed=7).items()}
+    tgt = torch.from_numpy(det_uniform(outs[0].numel(), 55).reshape(outs[0].shape)).to(DEV).abs() * 0.1
+
+    def loss_of(os_, kind):
+        if kind == 'noise':
+            return sum((o * torch.from_numpy(det_uniform(o.numel(), 100 + i).reshape(o.shape)).to(DEV)).sum() for i, o in enumerate(os_))
+        return sum(((o - tgt) ** 2).mean() * 1e3 for o in os_)
+
+    def nrm(a, b):
+        return float((a - b).double().norm() / b.double().norm().clamp_min(1e-30))
+
+    for kind in ('noise', 'mse'):
+        grads = {}
+        for mode in ('fp32', 'emul'):
+            sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+            loss_of(hourglass_forward(x, sd, stacks, round_bf16=(mode == 'emul'))[0], kind).backward()
+            grads[mode] = {k: v.grad for k, v in sd.items()}
+        net.zero_grad()
+        outs, _ = net(x)
+        loss_of(outs, kind).backward()
+        ours = {k: p.grad for k, p in net.named_parameters()}
+        if kind == 'noise':     # the fp32 torch-on-GPU reference agrees with the committed fixture of the reference itself
+            for k in g:
+                if k.startswith('grad.'):
+                    assert rel_err(grads['fp32'][k[5:]].cpu(), g[k]) < 5e-3
+        worst = []
+        for k in sd0:
+            e_ours, e_emul = nrm(ours[k], grads['fp32'][k]), nrm(grads['emul'][k], grads['fp32'][k])
+            worst.append((e_ours - 1.5 * e_emul, k, e_ours, e_emul))
+        worst.sort(reverse=True)
+        print('hourglass %d-stack %s: worst (ours, emulated-bf16) norm-rel grad errors:' % (stacks, kind),
+              [(k, '%.4f' % a, '%.4f' % b) for _, k, a, b in worst[:4]])
+        assert worst[0][0] < 2e-2, worst[0]
+        med = float(np.median([w[2] for w in worst]))
+        assert med < (0.25 if kind == 'noise' else 0.03)
