@@ -60,8 +60,19 @@ def lib():
     return _lib
 
 
+PROFILE = None     # set to a list to record (entry name, args, start event, end event) per call (bench.py's kernel shares)
+
+
 def call(name, *args):
     """Call an int-returning entry point; raise with the library's error text on failure."""
+    prof = PROFILE
+    if prof is not None:
+        import torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = getattr(lib(), name)(*args)
+    if prof is not None:
+        ev1.record()
+        prof.append((name, args, ev0, ev1))
     if rc != 0:
         raise SphereHandError('%s failed (%d): %s' % (name, rc, lib().sh_last_error().decode()))
