@@ -1,0 +1,451 @@
+// Hourglass convolutions, forward and data-gradient: persistent tcgen05 implicit-GEMM kernel (sm_100a).
+//
+// Replaces the cuDNN/ATen kernels behind every stride-1 nn.Conv2d of the reference network
+//   Bottleneck.conv1/conv2/conv3, downsample          /root/reference/network/hourglass.py:13-18, 125-128
+//   HourglassNet.fc / score / fc_ / score_            /root/reference/network/hourglass.py:110-114, 138-145
+// (the data gradient is the same launch on dY with the flipped/transposed weights of sh_pack_weights).
+//
+// Formulation: D[128 pixels, BN] += A[128 pixels, 64] * B[BN, 64]^T per (tap, 64-channel block); NHWC bf16 in HBM,
+// fp32 accumulators in TMEM.  A tile = one TMA box {64 ch, bw, bh, bn} of the 4-D activation tensor at spatial offset
+// (kw-1, kh-1): TMA's out-of-bounds zero fill IS the convolution padding (im2col staging without an im2col buffer).
+//
+// What bounds these layers on a B200 is bytes moved per pixel tile, not MMA issue, so the kernel is organised around
+// moving each byte once:
+//   * persistent: one CTA per SM walks pixel tiles (static round-robin); barriers / TMEM / descriptors set up once;
+//   * BN = ALL output channels (<= 256): the activation tile is fetched once, not once per 128-channel slice;
+//   * weights RESIDENT in shared memory whenever taps*Cin*BN*2 B fits (every 1x1 layer, the 64-channel 3x3): loaded
+//     once per CTA instead of once per tile; otherwise streamed next to the A tile in the same pipeline stage;
+//   * two TMEM accumulator buffers (2*BN columns): the epilogue of tile i overlaps the main loop of tile i+1;
+//   * epilogue through shared memory: the residual tile arrives by TMA (prefetched one 64-channel chunk ahead), each
+//     thread owns one pixel row (tcgen05.ld 32x32b), adds bias + residual, rounds to bf16, accumulates the GroupNorm
+//     statistics of the ROUNDED values (butterfly warp reduction -> one atomic per value), writes the swizzled staging
+//     tile in place and one elected thread issues a TMA store; a ring of staging slots lets loads / math / stores overlap;
+//   * TWO epilogue warp-groups (one per accumulator buffer, i.e. alternate tiles): a single warp per scheduler cannot hide
+//     its own instruction latencies, two tiles' epilogues in flight can.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue group 0 (even tiles of this CTA), warps 6..9 = epilogue group 1 (odd tiles).
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kBM = 128;           // pixels per tile = TMEM lanes
+constexpr int kBK = 64;            // channels per k-block = one 128-byte swizzle row
+constexpr int kThreads = 320;
+constexpr int kMaxStages = 8;
+constexpr int kMaxStg = 3;         // epilogue staging slots per warp-group (2 or 3)
+constexpr int kABytes = kBM * kBK * 2;          // 16 KB
+constexpr int kStgBytes = kBM * 64 * 2;         // 16 KB: 128 pixels x 64 channels bf16
+constexpr int kSmemLimit = 232448;              // 227 KB opt-in maximum per CTA
+
+struct ConvGeom {
+    int N, H, W;
+    int bw, bh, bn;                // TMA box (pixels): bw*bh*bn == 128
+    int tiles_w, tiles_h, num_tiles;
+    int taps;                      // 1 or 9
+    int kblocks;                   // Cin / 64
+    int cout;                      // real output channels
+    int cout_pad;                  // rows per tap in the weight matrix (== BN)
+    int y_ld;                      // channel stride of the bf16 output (0 = no bf16 output)
+    int groups;                    // GroupNorm groups of the statistics side output (0 = none)
+    int stages;                    // main-loop pipeline depth
+    int b_resident;                // weights loaded once per CTA
+    int has_res;                   // residual tile fetched by TMA
+    int nchunks;                   // 64-channel output chunks the epilogue processes
+    int nstg;                      // staging slots per epilogue group (2 or 3)
+};
+
+struct ConvPtrs {
+    const float* bias;             // [cout] or null
+    float* y_nchw;                 // [N,cout,H,W] fp32 or null
+    float* stats;                  // [N,groups,2] fp32 (sum, sum of squares), accumulated atomically
+};
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+struct TileCoord { int n0, h0, w0; };
+__device__ __forceinline__ TileCoord tile_coord(const ConvGeom& g, int tile) {
+    TileCoord t;
+    const int tw = tile % g.tiles_w; tile /= g.tiles_w;
+    const int th = tile % g.tiles_h; tile /= g.tiles_h;
+    t.n0 = tile * g.bn; t.h0 = th * g.bh; t.w0 = tw * g.bw;
+    return t;
+}
+
+// Butterfly (recursive-halving) warp reduction of V per-lane values over the R lanes that share an image: each split
+// step halves the values a lane is responsible for, so V values cost V-1 (+ log2(R/V)) shuffles instead of V*log2(R).
+template <int N, int O>
+struct Bfly {
+    static __device__ __forceinline__ void run(float* v, int lane, int& base) {
+        if constexpr (O >= 1) {
+            if constexpr (N > 1) {
+                constexpr int half = N / 2;
+                const bool upper = (lane & O) != 0;
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                    const float send = upper ? v[i] : v[i + half];
+                    const float keep = upper ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+                }
+                if (upper) base += half;
+                Bfly<half, O / 2>::run(v, lane, base);
+            } else {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], O);
+                Bfly<1, O / 2>::run(v, lane, base);
+            }
+        }
+    }
+};
+__host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x / 2); }
+
+// Per-(sample, group) sum / sum of squares of one thread row's 64 rounded channels (packed bf16 pairs), reduced over
+// the R lanes of the warp that belong to the same image; the lanes left owning a value issue one atomic each.
+template <int GS, int R>
+__device__ __forceinline__ void chunk_stats(const uint32_t (&packed)[32], bool row_ok, int lane, int cg, int cout,
+                                            float* __restrict__ stats_n) {
+    constexpr int V = 2 * (64 / GS);
+    float vals[V];
+#pragma unroll
+    for (int gi = 0; gi < 64 / GS; ++gi) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < GS / 2; ++j) {
+            const uint32_t pk = packed[gi * (GS / 2) + j];
+            const float x0 = __uint_as_float(pk << 16), x1 = __uint_as_float(pk & 0xffff0000u);
+            s1 += x0 + x1;
+            s2 += x0 * x0 + x1 * x1;
+        }
+        vals[2 * gi] = row_ok ? s1 : 0.f;
+        vals[2 * gi + 1] = row_ok ? s2 : 0.f;
+    }
+    int base = 0;
+    Bfly<V, R / 2>::run(vals, lane, base);
+    constexpr int split = ilog2(V) < ilog2(R) ? ilog2(V) : ilog2(R);
+    constexpr int left = V >> split;                       // values a lane still owns
+    constexpr int plain = ilog2(R) - split;                // trailing all-reduce steps: only lanes with those bits 0 write
+    if ((lane & ((1 << plain) - 1)) == 0 && row_ok) {
+#pragma unroll
+        for (int j = 0; j < left; ++j) {
+            const int idx = base + j;                       // = 2 * group-in-chunk + {0: sum, 1: sum of squares}
+            if (cg + (idx >> 1) * GS < cout) atomicAdd(stats_n + (cg / GS) * 2 + idx, vals[j]);
+        }
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmRes,
+                                                               const __grid_constant__ CUtensorMap tmOut,
+                                                               const ConvGeom g, const ConvPtrs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kBBytes = BN * kBK * 2;                       // one (tap, k-block) weight tile
+    const int num_k = g.taps * g.kblocks;
+    const int stage_bytes = kABytes + (g.b_resident ? 0 : kBBytes);
+    uint8_t* s_pipe = smem;
+    uint8_t* s_bres = s_pipe + g.stages * stage_bytes;          // resident weights (size 0 when streamed)
+    uint8_t* s_stg = s_bres + (g.b_resident ? num_k * kBBytes : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stg + 2 * g.nstg * kStgBytes);
+    uint64_t* full_bar = bars;                                  // [kMaxStages]
+    uint64_t* empty_bar = bars + kMaxStages;                    // [kMaxStages]
+    uint64_t* b_full = bars + 2 * kMaxStages;                   // [1]
+    uint64_t* acc_full = b_full + 1;                            // [2]
+    uint64_t* acc_empty = acc_full + 2;                         // [2]
+    uint64_t* res_full = acc_empty + 2;                         // [2 groups][kMaxStg]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2 * kMaxStg);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);    // [256]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (g.has_res) tma_prefetch_desc(&tmRes);
+        if (g.y_ld) tma_prefetch_desc(&tmOut);
+        for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(b_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+        for (int s = 0; s < 2 * kMaxStg; ++s) mbar_init(&res_full[s], 1);
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < 256; i += kThreads) s_bias[i] = (p.bias && i < g.cout) ? p.bias[i] : 0.f;
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one elected lane) =====================
+        if (lane == 0) {
+            if (g.b_resident) {
+                mbar_expect_tx(b_full, (uint32_t)(num_k * kBBytes));
+                for (int k = 0; k < num_k; ++k) {
+                    const int tap = k / g.kblocks, kb = k - tap * g.kblocks;
+                    tma_load_2d(s_bres + k * kBBytes, &tmB, b_full, kb * kBK, tap * g.cout_pad);
+                }
+            }
+            int it = 0;
+            for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+                const TileCoord t = tile_coord(g, tile);
+                for (int k = 0; k < num_k; ++k, ++it) {
+                    const int s = it % g.stages, ph = (it / g.stages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const int tap = k / g.kblocks, kb = k - tap * g.kblocks;
+                    const int dh = g.taps == 9 ? tap / 3 - 1 : 0, dw = g.taps == 9 ? tap % 3 - 1 : 0;
+                    uint8_t* a_dst = s_pipe + s * stage_bytes;
+                    mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                    tma_load_4d(a_dst, &tmA, &full_bar[s], kb * kBK, t.w0 + dw, t.h0 + dh, t.n0);
+                    if (!g.b_resident) tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], kb * kBK, tap * g.cout_pad);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected lane) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+            if (g.b_resident) mbar_wait(b_full, 0);
+            int it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tcount) {
+                const int buf = tcount & 1, aph = (tcount >> 1) & 1;
+                mbar_wait(&acc_empty[buf], aph ^ 1);            // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                for (int k = 0; k < num_k; ++k, ++it) {
+                    const int s = it % g.stages, ph = (it / g.stages) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(s_pipe + s * stage_bytes);
+                    const uint32_t b_addr = g.b_resident ? smem_u32(s_bres + k * kBBytes) : a_addr + kABytes;
+                    const uint64_t ad = umma_desc_kmajor_sw128(a_addr);
+                    const uint64_t bd = umma_desc_kmajor_sw128(b_addr);
+#pragma unroll
+                    for (int kk = 0; kk < kBK / 16; ++kk)       // +32 B inside the 128-byte swizzle row per K=16 step
+                        umma_bf16(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
+                    umma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
+                }
+                umma_commit(&acc_full[buf]);                    // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue warp-groups =====================
+        const int grp = (warp - 2) >> 2;                        // accumulator buffer / tile parity this group serves
+        const int quad = warp & 3;                              // TMEM lane quadrant this warp may read
+        const int m = quad * 32 + lane;                         // tile row = pixel (box order: w fastest, then h, n)
+        const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);   // issues this group's residual loads / output stores
+        const int px_per_img = g.bw * g.bh;
+        const int ln = m / px_per_img, lh = (m / g.bw) % g.bh, lw = m % g.bw;
+        const int gs = g.groups > 0 ? g.cout / g.groups : 64;   // channels per group
+        const uint32_t row_off = (uint32_t)m * 128u;
+        const uint32_t sw = (uint32_t)(m & 7);
+        uint8_t* my_stg = s_stg + grp * g.nstg * kStgBytes;
+        uint64_t* my_res = res_full + grp * kMaxStg;
+        const int first_tile = blockIdx.x + grp * gridDim.x, tile_step = 2 * gridDim.x;
+        int cc = 0;                                             // chunk counter of this group (staging ring position)
+        if (g.has_res && issuer && first_tile < g.num_tiles) {
+            const TileCoord t = tile_coord(g, first_tile);
+            mbar_expect_tx(&my_res[0], kStgBytes);
+            tma_load_4d(my_stg, &tmRes, &my_res[0], 0, t.w0, t.h0, t.n0);
+        }
+        int lt = 0;                                             // tiles this group has processed
+        for (int tile = first_tile; tile < g.num_tiles; tile += tile_step, ++lt) {
+            const TileCoord t = tile_coord(g, tile);
+            const int n = t.n0 + ln, h = t.h0 + lh, w = t.w0 + lw;
+            const bool row_ok = n < g.N;
+            mbar_wait(&acc_full[grp], lt & 1);
+            tc_fence_after();
+            for (int c = 0; c < g.nchunks; ++c, ++cc) {
+                const int slot = cc % g.nstg;
+                uint8_t* stg = my_stg + slot * kStgBytes;
+                if (issuer) {
+                    // the store that last used slot (cc+1) % nstg (chunk cc+1-nstg) must have finished reading its smem
+                    if (g.nstg == 3) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                    if (g.has_res) {
+                        int nc = c + 1, ntile = tile;
+                        if (nc == g.nchunks) { nc = 0; ntile = tile + tile_step; }
+                        if (ntile < g.num_tiles) {
+                            const TileCoord tn = tile_coord(g, ntile);
+                            const int ns = (cc + 1) % g.nstg;
+                            mbar_expect_tx(&my_res[ns], kStgBytes);
+                            tma_load_4d(my_stg + ns * kStgBytes, &tmRes, &my_res[ns], nc * 64, tn.w0, tn.h0, tn.n0);
+                        }
+                    }
+                }
+                uint32_t v[64];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * BN + c * 64);
+                tmem_ld32(taddr, v);
+                tmem_ld32(taddr + 32, v + 32);
+                if (g.has_res) mbar_wait(&my_res[slot], (cc / g.nstg) & 1);
+                tmem_ld_wait();
+                const int cg = c * 64;                          // first channel of this chunk
+                uint32_t packed[32];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {                   // 8 channels = one 16-byte smem chunk
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + s_bias[cg + q * 8 + e];
+                    if (g.has_res) {
+                        const uint4 rv = *reinterpret_cast<const uint4*>(stg + row_off + (((uint32_t)q ^ sw) << 4));
+                        const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            f[2 * e] += __uint_as_float(rr[e] << 16);
+                            f[2 * e + 1] += __uint_as_float(rr[e] & 0xffff0000u);
+                        }
+                    }
+                    if (p.y_nchw && row_ok) {
+                        const size_t hw = (size_t)g.H * g.W;
+                        float* o = p.y_nchw + ((size_t)n * g.cout + cg + q * 8) * hw + (size_t)h * g.W + w;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (cg + q * 8 + e < g.cout) o[(size_t)e * hw] = f[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                        packed[q * 4 + e] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    if (g.y_ld)
+                        *reinterpret_cast<uint4*>(stg + row_off + (((uint32_t)q ^ sw) << 4)) =
+                            make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+                }
+                if (g.y_ld) {
+                    fence_async_smem();                         // generic-proxy writes -> visible to the TMA store
+                    epi_bar(grp);
+                    if (issuer) {
+                        tma_store_4d(&tmOut, stg, cg, t.w0, t.h0, t.n0);
+                        bulk_commit();
+                    }
+                } else if (g.has_res) {
+                    epi_bar(grp);                               // everyone done reading the residual slot
+                }
+                if (p.stats && cg < g.cout) {
+                    // statistics of the ROUNDED values; a group never straddles a 64-channel chunk (gs | 64)
+                    float* sn = p.stats + (size_t)n * g.groups * 2;
+                    if (px_per_img >= 32) {
+                        if (gs == 4) chunk_stats<4, 32>(packed, row_ok, lane, cg, g.cout, sn);
+                        else if (gs == 8) chunk_stats<8, 32>(packed, row_ok, lane, cg, g.cout, sn);
+                        else if (gs == 16) chunk_stats<16, 32>(packed, row_ok, lane, cg, g.cout, sn);
+                        else chunk_stats<32, 32>(packed, row_ok, lane, cg, g.cout, sn);
+                    } else {                                    // 4x4 images: a warp covers two images
+                        if (gs == 4) chunk_stats<4, 16>(packed, row_ok, lane, cg, g.cout, sn);
+                        else if (gs == 8) chunk_stats<8, 16>(packed, row_ok, lane, cg, g.cout, sn);
+                        else if (gs == 16) chunk_stats<16, 16>(packed, row_ok, lane, cg, g.cout, sn);
+                        else chunk_stats<32, 16>(packed, row_ok, lane, cg, g.cout, sn);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[grp]);                       // 128 arrivals free the accumulator buffer
+        }
+        if (issuer) bulk_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+int make_act_tmap(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    return sh_make_tmap_bf16(m, base, 4, dims, strides, box);
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmRes, const CUtensorMap& tmOut,
+                const ConvGeom& g, const ConvPtrs& p, int grid, size_t smem, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        SH_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        attr = true;
+    }
+    conv_fwd_kernel<BN><<<grid, kThreads, smem, st>>>(tmA, tmB, tmRes, tmOut, g, p);
+    SH_CHECK_LAUNCH("conv_fwd_kernel");
+    return SH_OK;
+}
+
+}  // namespace
+
+// Implicit-GEMM convolution, stride 1, 'same' zero padding, NHWC bf16 in, fp32 accumulate.
+//   x        bf16 [N,H,W,Cin]           Cin % 64 == 0
+//   w        bf16 [taps, cout_pad, Cin] (tap-major, K contiguous); rows >= Cout must be zero; cout_pad in {64,128,256}
+//   residual bf16 [N,H,W,Cout] or null (Cout % 8 == 0)
+//   y        bf16 [N,H,W,y_ld] or null; y_nchw fp32 [N,Cout,H,W] or null; stats fp32 [N,groups,2] (accumulated) or null
+// The data-gradient is the same call on dY with flipped/transposed weights.
+SH_EXPORT int sh_conv_fwd(const void* x, const void* w, const void* bias, const void* residual, int N, int H, int W,
+                           int Cin, int Cout, int cout_pad, int taps, void* y, int y_ld, void* y_nchw, void* stats,
+                           int groups, void* stream) {
+    SH_REQUIRE(x && w && (y || y_nchw), "sh_conv_fwd: null pointer");
+    SH_REQUIRE(taps == 1 || taps == 9, "sh_conv_fwd: taps must be 1 or 9");
+    SH_REQUIRE(N >= 1 && is_pow2(H) && is_pow2(W) && H >= 4 && W >= 4, "sh_conv_fwd: H, W must be powers of two >= 4");
+    SH_REQUIRE(Cin % 64 == 0 && Cout >= 1 && cout_pad >= Cout && (cout_pad == 64 || cout_pad == 128 || cout_pad == 256),
+               "sh_conv_fwd: Cin %% 64 == 0 and cout_pad in {64,128,256} required (Cin=%d Cout=%d cout_pad=%d)", Cin, Cout, cout_pad);
+    SH_REQUIRE(!y || (y_ld % 8 == 0 && y_ld >= Cout && y_ld <= cout_pad), "sh_conv_fwd: y_ld must be a multiple of 8 in [Cout, cout_pad]");
+    SH_REQUIRE(!residual || Cout % 8 == 0, "sh_conv_fwd: residual needs Cout %% 8 == 0");
+    SH_REQUIRE(!stats || (groups > 0 && Cout % groups == 0 && (Cout / groups == 4 || Cout / groups == 8 || Cout / groups == 16 || Cout / groups == 32)),
+               "sh_conv_fwd: unsupported GroupNorm grouping");
+    cudaStream_t st = (cudaStream_t)stream;
+    ConvGeom g;
+    g.N = N; g.H = H; g.W = W;
+    g.bw = W < 16 ? W : 16;
+    g.bh = H < 128 / g.bw ? H : 128 / g.bw;
+    g.bn = 128 / (g.bw * g.bh);
+    SH_REQUIRE(g.bn <= 8, "sh_conv_fwd: image too small");
+    g.tiles_w = W / g.bw; g.tiles_h = H / g.bh;
+    g.num_tiles = g.tiles_w * g.tiles_h * ((N + g.bn - 1) / g.bn);
+    g.taps = taps; g.kblocks = Cin / 64; g.cout = Cout; g.cout_pad = cout_pad;
+    g.y_ld = y ? y_ld : 0;
+    g.groups = stats ? groups : 0;
+    g.has_res = residual ? 1 : 0;
+    const int top = (y && y_ld > Cout) ? y_ld : Cout;
+    g.nchunks = (top + 63) / 64;
+    // shared-memory plan: 2 epilogue groups x nstg staging slots, resident weights if they fit next to >= 2 A stages
+    const int num_k = taps * g.kblocks;
+    const int b_tile = cout_pad * 128;
+    const long resident = (long)num_k * b_tile;
+    size_t smem = 0;
+    for (g.nstg = kMaxStg; g.nstg >= 2; --g.nstg) {
+        const int fixed = 1024 /*alignment*/ + 2 * g.nstg * kStgBytes + 2048 /*barriers + bias*/;
+        const int avail = kSmemLimit - fixed;
+        if (resident + 2 * kABytes <= avail) {
+            g.b_resident = 1;
+            g.stages = (int)((avail - resident) / kABytes);
+        } else {
+            g.b_resident = 0;
+            g.stages = avail / (kABytes + b_tile);
+        }
+        if (g.stages > kMaxStages) g.stages = kMaxStages;
+        smem = (size_t)fixed + (size_t)g.stages * (kABytes + (g.b_resident ? 0 : b_tile)) + (g.b_resident ? resident : 0);
+        if (g.stages >= 3 || g.nstg == 2) break;
+    }
+    SH_REQUIRE(g.stages >= 2, "sh_conv_fwd: shared-memory plan failed");
+    ConvPtrs p{(const float*)bias, (float*)y_nchw, (float*)stats};
+    CUtensorMap tmA, tmB, tmRes, tmOut;
+    int rc = make_act_tmap(&tmA, x, N, H, W, Cin, g.bw, g.bh, g.bn);
+    if (rc) return rc;
+    const uint64_t wd[2] = {(uint64_t)Cin, (uint64_t)taps * cout_pad};
+    const uint64_t ws[1] = {(uint64_t)Cin * 2};
+    const uint32_t wb[2] = {64, (uint32_t)cout_pad};
+    rc = sh_make_tmap_bf16(&tmB, w, 2, wd, ws, wb);
+    if (rc) return rc;
+    tmRes = tmA;
+    tmOut = tmA;
+    if (residual) { rc = make_act_tmap(&tmRes, residual, N, H, W, Cout, g.bw, g.bh, g.bn); if (rc) return rc; }
+    if (y) { rc = make_act_tmap(&tmOut, y, N, H, W, y_ld, g.bw, g.bh, g.bn); if (rc) return rc; }
+    const int grid = g.num_tiles < SH_NUM_SMS ? g.num_tiles : SH_NUM_SMS;
+    if (cout_pad == 256) return launch_conv<256>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+    if (cout_pad == 128) return launch_conv<128>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+    return launch_conv<64>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+}
