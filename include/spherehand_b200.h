@@ -23,7 +23,7 @@ extern "C" {
 #endif
 
 /* ------------------------------------------------------------------------------------------------ library */
-int sh_abi_version(void);          /* 2 */
+int sh_abi_version(void);          /* 3 */
 const char* sh_build_arch(void);      /* "sm_100a" */
 const char* sh_last_error(void);
 long sh_launch_count(void);          /* kernel launches issued through this library since load */
@@ -132,8 +132,10 @@ int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, int x_C, i
 /* GroupNorm(G) + ReLU: y = relu(gn(x)); optional statistics of y for a following GroupNorm(G_out). */
 int sh_gn_relu_fwd(const void* x, const void* stats_in, const void* gamma, const void* beta, int N, int HW, int C,
                    int G, float eps, void* y, void* stats_out, int G_out, void* stream);
-/* Backward of the above: dx = d/dx (+ addend), dgamma/dbeta accumulated, optional column sum of dx (bias gradient of
- * the convolution that produced x).  red: scratch fp32 [N,G,2]. */
+/* Backward of the above in one pass over HBM: dx = d/dx (+ addend), dgamma/dbeta accumulated, optional column sum of dx
+ * (bias gradient of the convolution that produced x).  red: scratch of sh_gn_relu_bwd_scratch_words(N,G) 4-byte words
+ * (per-(n,g) partial sums + one arrive counter per sample; zeroed by the call).  HW*C <= 2M elements per sample. */
+size_t sh_gn_relu_bwd_scratch_words(int N, int G);
 int sh_gn_relu_bwd(const void* da, const void* x, const void* stats_in, const void* gamma, const void* beta,
                    const void* addend, int N, int HW, int C, int G, float eps, void* red, void* dgamma, void* dbeta,
                    void* dx, void* colsum, void* stream);
@@ -157,6 +159,10 @@ int sh_nhwc_to_nchw(const void* x, int N, int C, int HW, void* y, void* stream);
  * layout wb [taps,b_rows,b_cols] (flipped taps, transposed). */
 int sh_pack_weights(const void* w, int Cout, int Cin, int taps, int cout_pad, int cin_pad, int b_rows, int b_cols,
                     void* wf, void* wb, void* stream);
+/* The same for every convolution of a network in one launch.  flat: the flat fp32 parameter buffer; table int32 [n,10]
+ * (device) rows = (src offset in flat, Cout, Cin, taps, cout_pad, cin_pad, b_rows, b_cols, wf offset, wb offset or -1),
+ * offsets in elements; arena: bf16 buffer the wf/wb offsets index. */
+int sh_pack_weights_batch(const void* flat, const void* table, int n, void* arena, void* stream);
 int sh_unpack_wgrad(const void* dw, int Cout, int Cin, int taps, int cout_ld, int cin_ld, void* grad, void* stream);
 /* torch.optim.Adam step with L2 weight decay on flat fp32 buffers (network/engine.py:95-97); grad is read as g*grad_scale. */
 int sh_adam_step(void* p, const void* g, void* m, void* v, long n, float lr, float beta1, float beta2, float eps,

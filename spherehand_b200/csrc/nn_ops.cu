@@ -13,7 +13,7 @@
 // a separate reduction pass; kernels that produce an output-gradient tensor optionally accumulate its per-channel
 // column sum (the bias gradient of the producing convolution).  These kernels are HBM-bound: 16-byte vector
 // accesses (8 bf16 channels per thread), grid = (chunks, N) with >= 2 waves of 148 SMs.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -127,19 +127,59 @@ __global__ void __launch_bounds__(kT) gn_relu_fwd_kernel(const __nv_bfloat16* __
     }
 }
 
-// Backward pass 1: per-(n,g) sums  A = sum dxh, Bq = sum dxh * xhat  (dxh = dy*gamma, dy = da*[y>0]) and per-channel
-// dgamma = sum dy*xhat, dbeta = sum dy.  red[N,G,2] and dgamma/dbeta[C] are accumulated atomically.
-__global__ void __launch_bounds__(kT) gn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ x,
-                                                                const float* __restrict__ stats_in, const float* __restrict__ gamma,
-                                                                const float* __restrict__ beta, int HW, int C, int G, int ppb,
-                                                                float eps, float* __restrict__ red, float* __restrict__ dgamma,
-                                                                float* __restrict__ dbeta) {
+// Backward, ONE pass over HBM: a block stages its contiguous [ppb pixels x C] slab of x, da (and the addend) in shared
+// memory with 1-D bulk async copies (TMA), so every byte is read once and up to 96 KB per block are in flight.
+//   phase 1 (from smem): per-(n,g) sums A = sum dxh, Bq = sum dxh * xhat (dxh = dy*gamma, dy = da*[y>0]) and per-channel
+//            dgamma = sum dy*xhat, dbeta = sum dy;  block partials -> fp32 atomics into red[N,G,2], dgamma/dbeta[C];
+//   per-sample barrier: the blocks of one sample are adjacent in dispatch order (blockIdx.x fastest) and co-resident
+//            (<= 128 blocks per sample vs 592 resident), so a device-scope arrive counter + acquire spin is safe;
+//   phase 2 (from smem): dx = rstd * (dxh - A/m - xhat * Bq/m) (+ addend), written in place over the da slab and
+//            stored with one bulk async copy; optional column sum of the ROUNDED dx into colsum[C].
+constexpr int kBwdMaxElems = 8192;      // slab elements (pixels x channels): 16 KB bf16 per tensor, 48 KB per block
+constexpr int kBT = 128;                // threads per block: 4 blocks (16 warps) per SM in different phases
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ x,
+                                                             const float* __restrict__ stats_in, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const __nv_bfloat16* __restrict__ addend,
+                                                             int HW, int C, int G, int ppb, float eps, float* __restrict__ red,
+                                                             unsigned* __restrict__ counter, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx,
+                                                             float* __restrict__ colsum) {
+    extern __shared__ __align__(128) uint8_t bwd_smem[];
     __shared__ float s_mr[32 * 2];
     __shared__ float s_red[32 * 2];
     __shared__ float s_gb[2][256];
+    __shared__ float s_cs[256];
+    __shared__ __align__(8) uint64_t s_bar[2];
     const int n = blockIdx.y;
+    const int p0 = blockIdx.x * ppb;
+    const int npix = min(ppb, HW - p0);
+    const uint32_t bytes = (uint32_t)npix * C * 2;
+    const uint32_t slab = (uint32_t)ppb * C * 2;
+    uint8_t* s_x = bwd_smem;
+    uint8_t* s_da = bwd_smem + slab;
+    uint8_t* s_add = bwd_smem + 2 * slab;
+    const size_t goff = ((size_t)n * HW + p0) * C;
     const int gs = C / G;
     const float cnt_inv = 1.f / ((float)HW * gs);
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
     if (threadIdx.x < G) {
         const float s1 = stats_in[((size_t)n * G + threadIdx.x) * 2], s2 = stats_in[((size_t)n * G + threadIdx.x) * 2 + 1];
         const float mean = s1 * cnt_inv;
@@ -148,107 +188,135 @@ __global__ void __launch_bounds__(kT) gn_relu_bwd_reduce_kernel(const __nv_bfloa
         s_mr[threadIdx.x * 2 + 1] = rsqrtf(var + eps);
     }
     if (threadIdx.x < 64) s_red[threadIdx.x] = 0.f;
-    for (int i = threadIdx.x; i < 512; i += kT) (&s_gb[0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < 512; i += kBT) (&s_gb[0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < 256; i += kBT) s_cs[i] = 0.f;
     __syncthreads();
-    const Walk w = make_walk(C);
-    const int c0 = w.cv * 8;
-    float ga[8], be[8], mu[8], rs[8], dg[8], db[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        ga[e] = gamma[c0 + e]; be[e] = beta[c0 + e];
-        mu[e] = s_mr[((c0 + e) / gs) * 2]; rs[e] = s_mr[((c0 + e) / gs) * 2 + 1];
-        dg[e] = 0.f; db[e] = 0.f;
-    }
-    float A[2] = {0.f, 0.f}, Bq[2] = {0.f, 0.f};
-    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
-    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
-        const size_t o = ((size_t)n * HW + pp) * C + c0;
-        const bf8 xv = load8(x + o);
-        const bf8 gv = load8(da + o);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float xh = (xv.v[e] - mu[e]) * rs[e];
-            const float dy = (xh * ga[e] + be[e] > 0.f) ? gv.v[e] : 0.f;
-            dg[e] += dy * xh;
-            db[e] += dy;
-            const float dxh = dy * ga[e];
-            const int h = (gs == 4) ? (e >> 2) : 0;
-            A[h] += dxh;
-            Bq[h] += dxh * xh;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar[0], 2 * bytes);
+        for (uint32_t o = 0; o < bytes; o += 4096) {          // 4 KB pieces: several bulk requests in flight per tensor
+            const uint32_t b = min(4096u, bytes - o);
+            bulk_g2s(s_x + o, reinterpret_cast<const uint8_t*>(x + goff) + o, b, &s_bar[0]);
+            bulk_g2s(s_da + o, reinterpret_cast<const uint8_t*>(da + goff) + o, b, &s_bar[0]);
+        }
+        if (addend) {
+            mbar_expect_tx(&s_bar[1], bytes);
+            for (uint32_t o = 0; o < bytes; o += 4096)
+                bulk_g2s(s_add + o, reinterpret_cast<const uint8_t*>(addend + goff) + o, min(4096u, bytes - o), &s_bar[1]);
         }
     }
-    if (gs == 4) {
-        atomicAdd(&s_red[(c0 / 4) * 2], A[0]); atomicAdd(&s_red[(c0 / 4) * 2 + 1], Bq[0]);
-        atomicAdd(&s_red[(c0 / 4 + 1) * 2], A[1]); atomicAdd(&s_red[(c0 / 4 + 1) * 2 + 1], Bq[1]);
-    } else {
-        atomicAdd(&s_red[(c0 / gs) * 2], A[0]); atomicAdd(&s_red[(c0 / gs) * 2 + 1], Bq[0]);
-    }
+    const int vecs = C / 8, rows = kBT / vecs;
+    const int cv = threadIdx.x % vecs, r0 = threadIdx.x / vecs;
+    const int c0 = cv * 8;
+    // y = x*ka + kb (the ReLU argument), xhat = x*rs + nm
+    float ka[8], kb[8], rs[8], nm[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { atomicAdd(&s_gb[0][c0 + e], dg[e]); atomicAdd(&s_gb[1][c0 + e], db[e]); }
-    __syncthreads();
-    if (threadIdx.x < G * 2) atomicAdd(&red[(size_t)n * G * 2 + threadIdx.x], s_red[threadIdx.x]);
-    for (int c = threadIdx.x; c < C; c += kT) { atomicAdd(&dgamma[c], s_gb[0][c]); atomicAdd(&dbeta[c], s_gb[1][c]); }
-}
-
-// Backward pass 2: dx = rstd * (dxh - A/m - xhat * Bq/m) (+ addend);  optional column sum of dx into colsum[C].
-__global__ void __launch_bounds__(kT) gn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ x,
-                                                               const float* __restrict__ stats_in, const float* __restrict__ red,
-                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                               const __nv_bfloat16* __restrict__ addend, int HW, int C, int G, int ppb,
-                                                               float eps, __nv_bfloat16* __restrict__ dx, float* __restrict__ colsum) {
-    __shared__ float s_mr[32 * 4];
-    __shared__ float s_cs[256];
-    const int n = blockIdx.y;
-    const int gs = C / G;
-    const float cnt_inv = 1.f / ((float)HW * gs);
-    if (threadIdx.x < G) {
-        const float s1 = stats_in[((size_t)n * G + threadIdx.x) * 2], s2 = stats_in[((size_t)n * G + threadIdx.x) * 2 + 1];
-        const float mean = s1 * cnt_inv;
-        const float var = fmaxf(s2 * cnt_inv - mean * mean, 0.f);
-        s_mr[threadIdx.x * 4] = mean;
-        s_mr[threadIdx.x * 4 + 1] = rsqrtf(var + eps);
-        s_mr[threadIdx.x * 4 + 2] = red[((size_t)n * G + threadIdx.x) * 2] * cnt_inv;
-        s_mr[threadIdx.x * 4 + 3] = red[((size_t)n * G + threadIdx.x) * 2 + 1] * cnt_inv;
+    for (int e = 0; e < 8; ++e) {
+        const float mu = s_mr[((c0 + e) / gs) * 2];
+        rs[e] = s_mr[((c0 + e) / gs) * 2 + 1];
+        nm[e] = -mu * rs[e];
+        ka[e] = rs[e] * gamma[c0 + e];
+        kb[e] = fmaf(nm[e], gamma[c0 + e], beta[c0 + e]);
     }
-    if (threadIdx.x < 256) s_cs[threadIdx.x] = 0.f;
+    mbar_wait(&s_bar[0], 0);
+    {
+        float dg[8], db[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { dg[e] = 0.f; db[e] = 0.f; }
+#pragma unroll 2
+        for (int pp = r0; pp < npix; pp += rows) {
+            const uint32_t o = ((uint32_t)pp * C + c0) * 2;
+            const bf8 xv = load8(reinterpret_cast<const __nv_bfloat16*>(s_x + o));
+            const bf8 gv = load8(reinterpret_cast<const __nv_bfloat16*>(s_da + o));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float y = fmaf(xv.v[e], ka[e], kb[e]);
+                const float xh = fmaf(xv.v[e], rs[e], nm[e]);
+                const float dy = y > 0.f ? gv.v[e] : 0.f;
+                dg[e] = fmaf(dy, xh, dg[e]);
+                db[e] += dy;
+            }
+        }
+        // per-group sums from the per-channel ones: A = sum gamma*dbeta_c, Bq = sum gamma*dgamma_c
+        float A[2] = {0.f, 0.f}, Bq[2] = {0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float ga = gamma[c0 + e];
+            const int h = (gs == 4) ? (e >> 2) : 0;
+            A[h] = fmaf(ga, db[e], A[h]);
+            Bq[h] = fmaf(ga, dg[e], Bq[h]);
+        }
+        if (gs == 4) {
+            atomicAdd(&s_red[(c0 / 4) * 2], A[0]); atomicAdd(&s_red[(c0 / 4) * 2 + 1], Bq[0]);
+            atomicAdd(&s_red[(c0 / 4 + 1) * 2], A[1]); atomicAdd(&s_red[(c0 / 4 + 1) * 2 + 1], Bq[1]);
+        } else {
+            atomicAdd(&s_red[(c0 / gs) * 2], A[0]); atomicAdd(&s_red[(c0 / gs) * 2 + 1], Bq[0]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { atomicAdd(&s_gb[0][c0 + e], dg[e]); atomicAdd(&s_gb[1][c0 + e], db[e]); }
+    }
     __syncthreads();
-    const Walk w = make_walk(C);
-    const int c0 = w.cv * 8;
-    float ga[8], be[8], mu[8], rs[8], mA[8], mB[8], cs[8];
+    if (gridDim.x > 1) {
+        if (threadIdx.x < G * 2) {
+            atomicAdd(&red[(size_t)n * G * 2 + threadIdx.x], s_red[threadIdx.x]);
+            __threadfence();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(&counter[n], 1u);
+    }
+    for (int c = threadIdx.x; c < C; c += kBT) { atomicAdd(&dgamma[c], s_gb[0][c]); atomicAdd(&dbeta[c], s_gb[1][c]); }
+    if (gridDim.x > 1) {
+        if (threadIdx.x == 0)
+            while (ld_acquire_u32(&counter[n]) < gridDim.x) __nanosleep(32);
+        __syncthreads();
+        if (threadIdx.x < G * 2) s_red[threadIdx.x] = __ldcg(&red[(size_t)n * G * 2 + threadIdx.x]);
+        __syncthreads();
+    }
+    // dx = dy*ka + x*k2 + k3 (+ addend):  rstd*(dy*gamma - A/m - xhat*Bq/m) with xhat = x*rs + nm folded into k2, k3
+    float k2[8], k3[8], cs[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int g = (c0 + e) / gs;
-        ga[e] = gamma[c0 + e]; be[e] = beta[c0 + e];
-        mu[e] = s_mr[g * 4]; rs[e] = s_mr[g * 4 + 1]; mA[e] = s_mr[g * 4 + 2]; mB[e] = s_mr[g * 4 + 3];
+        const float mA = s_red[g * 2] * cnt_inv, mB = s_red[g * 2 + 1] * cnt_inv;
+        k2[e] = -rs[e] * rs[e] * mB;
+        k3[e] = -rs[e] * fmaf(nm[e], mB, mA);
         cs[e] = 0.f;
     }
-    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
-    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
-        const size_t o = ((size_t)n * HW + pp) * C + c0;
-        const bf8 xv = load8(x + o);
-        const bf8 gv = load8(da + o);
+    if (addend) mbar_wait(&s_bar[1], 0);
+#pragma unroll 2
+    for (int pp = r0; pp < npix; pp += rows) {
+        const uint32_t o = ((uint32_t)pp * C + c0) * 2;
+        const bf8 xv = load8(reinterpret_cast<const __nv_bfloat16*>(s_x + o));
+        const bf8 gv = load8(reinterpret_cast<const __nv_bfloat16*>(s_da + o));
         bf8 r;
-        if (addend) r = load8(addend + o);
+        if (addend) r = load8(reinterpret_cast<const __nv_bfloat16*>(s_add + o));
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float xh = (xv.v[e] - mu[e]) * rs[e];
-            const float dy = (xh * ga[e] + be[e] > 0.f) ? gv.v[e] : 0.f;
-            float d = rs[e] * (dy * ga[e] - mA[e] - xh * mB[e]);
+            const float y = fmaf(xv.v[e], ka[e], kb[e]);
+            const float dy = y > 0.f ? gv.v[e] : 0.f;
+            float d = fmaf(dy, ka[e], fmaf(xv.v[e], k2[e], k3[e]));
             if (addend) d += r.v[e];
             r.v[e] = d;
         }
-        store8(dx + o, r);
+        store8(reinterpret_cast<__nv_bfloat16*>(s_da + o), r);
         if (colsum) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) cs[e] += r.v[e];
         }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (colsum) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[c0 + e], cs[e]);
-        __syncthreads();
-        for (int c = threadIdx.x; c < C; c += kT) atomicAdd(&colsum[c], s_cs[c]);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (uint32_t o = 0; o < bytes; o += 4096)
+            bulk_s2g(reinterpret_cast<uint8_t*>(dx + goff) + o, s_da + o, min(4096u, bytes - o));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (colsum)
+        for (int c = threadIdx.x; c < C; c += kBT) atomicAdd(&colsum[c], s_cs[c]);
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ pooling / up-sampling
@@ -631,6 +699,29 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int C
     }
 }
 
+// All convolutions of a network in ONE launch: blockIdx.y = table row (src offset into the flat fp32 parameter buffer,
+// Cout, Cin, taps, cout_pad, cin_pad, b_rows, b_cols, wf offset, wb offset (-1 = none) into the bf16 arena).
+__global__ void pack_weights_batch_kernel(const float* __restrict__ flat, const int* __restrict__ table,
+                                          __nv_bfloat16* __restrict__ arena) {
+    const int* t = table + blockIdx.y * 10;
+    const float* w = flat + t[0];
+    const int Cout = t[1], Cin = t[2], taps = t[3], cout_pad = t[4], cin_pad = t[5], b_rows = t[6], b_cols = t[7];
+    __nv_bfloat16* wf = arena + t[8];
+    const long nf = (long)taps * cout_pad * cin_pad;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += (long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin_pad), co = (int)((i / cin_pad) % cout_pad), tap = (int)(i / ((long)cin_pad * cout_pad));
+        wf[i] = __float2bfloat16((co < Cout && ci < Cin) ? w[((size_t)co * Cin + ci) * taps + tap] : 0.f);
+    }
+    if (t[9] >= 0) {
+        __nv_bfloat16* wb = arena + t[9];
+        const long nb = (long)taps * b_rows * b_cols;
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += (long)gridDim.x * blockDim.x) {
+            const int co = (int)(i % b_cols), ci = (int)((i / b_cols) % b_rows), tap = (int)(i / ((long)b_cols * b_rows));
+            wb[i] = __float2bfloat16((co < Cout && ci < Cin) ? w[((size_t)co * Cin + ci) * taps + (taps - 1 - tap)] : 0.f);
+        }
+    }
+}
+
 // dW fp32 [tap][Cout][Cin] (tensor-core accumulation layout) -> grad fp32 [Cout][Cin][kh][kw] (the reference layout)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, int Cout, int Cin, int taps, int cout_ld, int cin_ld,
                                     float* __restrict__ grad) {
@@ -683,7 +774,10 @@ SH_EXPORT int sh_gn_relu_fwd(const void* x, const void* stats_in, const void* ga
     return SH_OK;
 }
 
-// red: fp32 [N,G,2] scratch (zeroed here); dgamma/dbeta accumulated (caller zeroes once per step)
+// Scratch words (4 bytes each) sh_gn_relu_bwd needs in `red`: the per-(n,g) sums plus one arrive counter per sample.
+SH_EXPORT size_t sh_gn_relu_bwd_scratch_words(int N, int G) { return (size_t)N * G * 2 + (size_t)N; }
+
+// red: scratch of sh_gn_relu_bwd_scratch_words(N,G) words (zeroed here); dgamma/dbeta accumulated (caller zeroes once per step)
 SH_EXPORT int sh_gn_relu_bwd(const void* da, const void* x, const void* stats_in, const void* gamma, const void* beta,
                               const void* addend, int N, int HW, int C, int G, float eps, void* red, void* dgamma, void* dbeta,
                               void* dx, void* colsum, void* stream) {
@@ -692,18 +786,27 @@ SH_EXPORT int sh_gn_relu_bwd(const void* da, const void* x, const void* stats_in
     SH_REQUIRE(G >= 1 && G <= 32 && C % G == 0 && (C / G) % 4 == 0, "sh_gn_relu_bwd: bad grouping");
     if (N == 0) return SH_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    SH_CUDA(cudaMemsetAsync(red, 0, (size_t)N * G * 2 * sizeof(float), st));
-    const int ppb = pick_ppb(HW, N, kT / (C / 8));
-    dim3 grid(sh_div_up(HW, ppb), N);
-    gn_relu_bwd_reduce_kernel<<<grid, kT, 0, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)x, (const float*)stats_in,
-                                                   (const float*)gamma, (const float*)beta, HW, C, G, ppb, eps, (float*)red,
-                                                   (float*)dgamma, (float*)dbeta);
-    SH_CHECK_LAUNCH("gn_relu_bwd_reduce_kernel");
-    gn_relu_bwd_apply_kernel<<<grid, kT, 0, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)x, (const float*)stats_in,
-                                                  (const float*)red, (const float*)gamma, (const float*)beta,
-                                                  (const __nv_bfloat16*)addend, HW, C, G, ppb, eps, (__nv_bfloat16*)dx,
-                                                  (float*)colsum);
-    SH_CHECK_LAUNCH("gn_relu_bwd_apply_kernel");
+    SH_REQUIRE(kBT % (C / 8) == 0, "sh_gn_relu_bwd: C / 8 must divide 128");
+    const int rows = kBT / (C / 8);
+    // pixels per block: the largest slab that fits (16 KB per tensor), halved while that leaves SMs idle
+    int ppb = kBwdMaxElems / C;
+    if (ppb > HW) ppb = HW;
+    while (ppb > 2 * rows && (long)N * ((HW + ppb - 1) / ppb) < 2L * SH_NUM_SMS) ppb = (ppb + 1) / 2;
+    const int nblk = sh_div_up(HW, ppb);
+    SH_REQUIRE(nblk <= 128, "sh_gn_relu_bwd: sample too large for the co-resident per-sample barrier (HW*C <= 2M elements)");
+    SH_CUDA(cudaMemsetAsync(red, 0, sh_gn_relu_bwd_scratch_words(N, G) * 4, st));
+    const size_t smem = (size_t)ppb * C * 2 * (addend ? 3 : 2);
+    static bool attr = false;
+    if (!attr) {
+        SH_CUDA(cudaFuncSetAttribute(gn_relu_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kBwdMaxElems * 2));
+        attr = true;
+    }
+    dim3 grid(nblk, N);
+    gn_relu_bwd_kernel<<<grid, kBT, smem, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)x, (const float*)stats_in,
+                                               (const float*)gamma, (const float*)beta, (const __nv_bfloat16*)addend, HW, C, G, ppb,
+                                               eps, (float*)red, (unsigned*)red + (size_t)N * G * 2, (float*)dgamma, (float*)dbeta,
+                                               (__nv_bfloat16*)dx, (float*)colsum);
+    SH_CHECK_LAUNCH("gn_relu_bwd_kernel");
     return SH_OK;
 }
 
@@ -836,6 +939,15 @@ SH_EXPORT int sh_pack_weights(const void* w, int Cout, int Cin, int taps, int co
     pack_weights_kernel<<<sh_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)w, Cout, Cin, taps, cout_pad, cin_pad,
                                                                             b_rows, b_cols, (__nv_bfloat16*)wf, (__nv_bfloat16*)wb);
     SH_CHECK_LAUNCH("pack_weights_kernel");
+    return SH_OK;
+}
+
+SH_EXPORT int sh_pack_weights_batch(const void* flat, const void* table, int n, void* arena, void* stream) {
+    SH_REQUIRE(flat && table && arena && n >= 0, "sh_pack_weights_batch: bad arguments");
+    if (n == 0) return SH_OK;
+    pack_weights_batch_kernel<<<dim3(24, n), 256, 0, (cudaStream_t)stream>>>((const float*)flat, (const int*)table,
+                                                                            (__nv_bfloat16*)arena);
+    SH_CHECK_LAUNCH("pack_weights_batch_kernel");
     return SH_OK;
 }
 

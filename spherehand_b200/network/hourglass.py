@@ -53,10 +53,13 @@ class Hourglass(nn.Module):
 
 class _Tensor:
     """NHWC bf16 activation + the fp32 [N,16,2] statistics the consuming GroupNorm needs."""
-    __slots__ = ('buf', 'stats', 'H', 'W', 'C')
+    __slots__ = ('buf', 'stats', 'H', 'W', 'C', 'bias_grads')
 
     def __init__(self, buf, stats, H, W, C):
         self.buf, self.stats, self.H, self.W, self.C = buf, stats, H, W, C
+        # fp32 gradient views that equal the per-channel column sum of dL/d(this tensor): the biases of the convolutions
+        # whose outputs sum to it.  The kernel that finalises dL/d(tensor) fuses that column sum (`_Run.cs`).
+        self.bias_grads = []
 
 
 class HourglassNet(nn.Module):
@@ -114,6 +117,41 @@ class HourglassNet(nn.Module):
         self._wcache = {}
         return flat
 
+    def _conv_geometry(self, conv):
+        Cout, Cin, k, _ = conv.weight.shape
+        taps = k * k
+        cout_pad = _ceil(Cout, 128) if Cout > 64 else 64
+        cin_pad = _ceil(Cin, 64) if Cin % 64 else Cin
+        if Cin == self.num_outputs:
+            cin_pad = 128
+        # data-gradient GEMM: rows = Cin (padded to its N tile), cols = Cout (padded to a K multiple of 64)
+        b_rows = _ceil(Cin, 128) if Cin > 64 else 64
+        b_cols = _ceil(Cout, 64)
+        if Cout == self.num_outputs:
+            b_cols = 128
+        return Cout, Cin, taps, cout_pad, cin_pad, b_rows, b_cols
+
+    def pack_all_weights(self):
+        """fp32 masters -> bf16 tensor-core layouts of every stride-1 convolution, one launch (sh_pack_weights_batch)."""
+        self.flatten_parameters()
+        if not self._wcache:
+            convs = [m for m in self.modules() if isinstance(m, nn.Conv2d) and m is not self.conv1]
+            rows, off = [], 0
+            for c in convs:
+                Cout, Cin, taps, cout_pad, cin_pad, b_rows, b_cols = self._conv_geometry(c)
+                nf, nb = taps * cout_pad * cin_pad, taps * b_rows * b_cols
+                rows.append([self._offsets[id(c.weight)][0], Cout, Cin, taps, cout_pad, cin_pad, b_rows, b_cols, off, off + nf])
+                off += nf + nb
+            dev = self._flat.device
+            self._warena = torch.empty(off, device=dev, dtype=BF16)
+            self._wtable = torch.tensor(rows, dtype=torch.int32, device=dev)
+            for c, r in zip(convs, rows):
+                _, Cout, Cin, taps, cout_pad, cin_pad, b_rows, b_cols, o_f, o_b = r
+                wf = self._warena[o_f:o_b].view(taps, cout_pad, cin_pad)
+                wb = self._warena[o_b:o_b + taps * b_rows * b_cols].view(taps, b_rows, b_cols)
+                self._wcache[id(c)] = (wf, wb, cout_pad, cin_pad, b_rows, b_cols)
+        ops.pack_weights_batch(self._flat, self._wtable, self._warena)
+
     def grad_view(self, p):
         off, n = self._offsets[id(p)]
         return self._flat_grad[off:off + n].view(p.shape)
@@ -134,6 +172,7 @@ class HourglassNet(nn.Module):
             x = x[:, 0]
         x = x.contiguous().float()
         N, S = x.shape[0], x.shape[-1]
+        self.pack_all_weights()
         ctx = _Run(self, N, x.device)
         scores, latents = ctx.forward(x, S)
         self._last_run = ctx
@@ -179,31 +218,27 @@ class _Run:
         self.stats_used += 1
         return s
 
+    def cs(self, t):
+        """Column-sum target for the kernel that finalises dL/dt (None if no bias hangs off t)."""
+        return t.bias_grads[0] if t.bias_grads else None
+
+    def cs_done(self, t):
+        for extra in t.bias_grads[1:]:
+            extra.copy_(t.bias_grads[0])
+
+    def cs_fallback(self, t, dbuf):
+        """dL/dt was produced by a kernel without a fused column sum (a convolution data-gradient)."""
+        if t.bias_grads:
+            ops.colsum(dbuf, self.N, t.H * t.W, t.C, t.bias_grads[0])
+            self.cs_done(t)
+
     def act(self, H, W, C, stats=True):
         buf = torch.empty((self.N, H, W, C), device=self.dev, dtype=BF16)
         return _Tensor(buf, self.new_stats() if stats else None, H, W, C)
 
-    def packed(self, conv, need_bwd=True):
-        """bf16 forward / data-gradient weight layouts of a conv, re-packed from the fp32 master every forward."""
-        Cout, Cin, k, _ = conv.weight.shape
-        taps = k * k
-        cout_pad = _ceil(Cout, 128) if Cout > 64 else 64
-        cin_pad = _ceil(Cin, 64) if Cin % 64 else Cin
-        if Cin == self.net.num_outputs:
-            cin_pad = 128
-        key = id(conv)
-        if key not in self.net._wcache:
-            wf = torch.empty((taps, cout_pad, cin_pad), device=self.dev, dtype=BF16)
-            # data-gradient GEMM: rows = Cin (padded to its N tile), cols = Cout (padded to a K multiple of 64)
-            b_rows = _ceil(Cin, 128) if Cin > 64 else 64
-            b_cols = _ceil(Cout, 64)
-            if Cout == self.net.num_outputs:
-                b_cols = 128
-            wb = torch.empty((taps, b_rows, b_cols), device=self.dev, dtype=BF16) if need_bwd else None
-            self.net._wcache[key] = (wf, wb, cout_pad, cin_pad, b_rows, b_cols)
-        wf, wb, cout_pad, cin_pad, b_rows, b_cols = self.net._wcache[key]
-        ops.pack_weights(conv.weight.data, Cout, Cin, taps, cout_pad, cin_pad, wf, wb, b_rows, b_cols)
-        return wf, wb, cout_pad, cin_pad, b_rows, b_cols
+    def packed(self, conv):
+        """bf16 forward / data-gradient weight layouts of a conv (packed from the fp32 masters at the start of this forward)."""
+        return self.net._wcache[id(conv)]
 
     # -------------------------------------------------------------- layers
     def conv(self, conv, a, a_C, out, residual=None, y_nchw=None, want_stats=True):
@@ -240,15 +275,16 @@ class _Run:
         net = self.net
 
         def bwd(da, addend=None, colsum=None):
-            red = torch.empty((N, G, 2), device=self.dev, dtype=torch.float32)
+            red = ops.gn_relu_bwd_scratch(N, G, self.dev)
             dx = torch.empty_like(x.buf)
             ops.gn_relu_bwd(da, x.buf, x.stats, gn.weight.data, gn.bias.data, N, x.H * x.W, x.C, G, red,
                             net.grad_view(gn.weight), net.grad_view(gn.bias), dx, addend, colsum)
             return dx
         return a, st, bwd
 
-    def bottleneck(self, blk, x):
-        """Pre-activation bottleneck (hourglass.py:23-41).  x: _Tensor with stats -> _Tensor with stats."""
+    def bottleneck(self, blk, x, x_final=True):
+        """Pre-activation bottleneck (hourglass.py:23-41).  x: _Tensor with stats -> _Tensor with stats.
+        x_final: the gradient this block returns is the whole dL/dx (no other consumer of x adds to it afterwards)."""
         net, N = self.net, self.N
         planes = blk.conv1.weight.shape[0]
         H, W = x.H, x.W
@@ -267,26 +303,29 @@ class _Run:
         else:
             d_b, res_buf = None, x.buf
         c3_b = self.conv(blk.conv3, a3, planes, out, residual=res_buf)
+        # bias gradients of conv3 (and of the downsample conv, which sees the same output gradient) = colsum(dL/dout)
+        out.bias_grads = [net.grad_view(blk.conv3.bias)] + ([net.grad_view(blk.downsample[0].bias)] if d_b is not None else [])
 
         def bwd(dout):
-            # bias gradients of conv3 (and of the downsample conv, which sees the same output gradient)
-            ops.colsum(dout, N, H * W, planes * 2, net.grad_view(blk.conv3.bias))
-            if d_b is not None:
-                net.grad_view(blk.downsample[0].bias).copy_(net.grad_view(blk.conv3.bias))
+            """dout = dL/dout, its column sum already delivered to out.bias_grads by whoever produced it."""
             da3 = c3_b(dout, planes * 2)
             dt2 = gn3_b(da3, colsum=net.grad_view(blk.conv2.bias))
             da2 = c2_b(dt2, planes)
             dt1 = gn2_b(da2, colsum=net.grad_view(blk.conv1.bias))
             da1 = c1_b(dt1, planes)
             dres = d_b(dout, planes * 2) if d_b is not None else dout
-            return gn1_b(da1, addend=dres)
+            dx = gn1_b(da1, addend=dres, colsum=self.cs(x) if x_final else None)
+            if x_final:
+                self.cs_done(x)
+            return dx
         return out, bwd
 
-    def hourglass(self, hgm, n, x):
-        """hourglass.py:68-82.  Returns (out, latent, backward)."""
+    def hourglass(self, hgm, n, x, defer_cs=False):
+        """hourglass.py:68-82.  Returns (out, latent, backward).  defer_cs: the caller adds another gradient to dL/dx
+        and takes its column sum there."""
         N = self.N
         lvl = hgm.hg[n - 1]
-        up1, up1_b = self.bottleneck(lvl[0][0], x)
+        up1, up1_b = self.bottleneck(lvl[0][0], x, x_final=False)     # dL/dx is finalised by the max-pool backward
         pooled = self.act(x.H // 2, x.W // 2, x.C)
         ops.maxpool_fwd(x.buf, N, pooled.H, pooled.W, x.C, pooled.buf, pooled.stats, 16)
         low1, low1_b = self.bottleneck(lvl[1][0], pooled)
@@ -298,16 +337,21 @@ class _Run:
         low3, low3_b = self.bottleneck(lvl[2][0], low2)
         out = self.act(x.H, x.W, x.C)
         ops.upsample_add_fwd(up1.buf, low3.buf, N, low3.H, low3.W, x.C, out.buf, out.stats, 16)
+        out.bias_grads = up1.bias_grads                 # dL/dup1 == dL/dout
 
         def bwd(dout, dlatent=None):
             dlow3 = torch.empty_like(low3.buf)
-            ops.upsample_bwd(dout, N, low3.H, low3.W, x.C, dlow3)
+            ops.upsample_bwd(dout, N, low3.H, low3.W, x.C, dlow3, colsum=self.cs(low3))
+            self.cs_done(low3)
             dlow2 = low3_b(dlow3)
             dlow1 = low2_b(dlow2)
             dpooled = low1_b(dlow1)
             dx_a = up1_b(dout)
             dx = torch.empty_like(x.buf)
-            ops.maxpool_bwd(dpooled, x.buf, N, pooled.H, pooled.W, x.C, dx, addend=dx_a)
+            ops.maxpool_bwd(dpooled, x.buf, N, pooled.H, pooled.W, x.C, dx, addend=dx_a,
+                            colsum=None if defer_cs else self.cs(x))
+            if not defer_cs:
+                self.cs_done(x)
             return dx
         return out, latent, bwd
 
@@ -332,13 +376,14 @@ class _Run:
         h = H2
         scores, latents, stack_b = [], [], []
         for i in range(net.num_stacks):
-            y, latent, hg_b = self.hourglass(net.hg[i], 2, x)
+            last = i == net.num_stacks - 1
+            # (not last: dL/dx also receives dL/dx_next through the residual chain; the add below takes the column sum)
+            y, latent, hg_b = self.hourglass(net.hg[i], 2, x, defer_cs=not last)
             y, res_b = self.bottleneck(net.res[i][0], y)
             f = self.act(h, h, 256)
             fc_b = self.conv(net.fc[i][0], y.buf, 256, f)
             yf_buf, _, fcgn_b = self.gn_relu(f, net.fc[i][1])
             score = torch.empty((N, K, h, h), device=self.dev, dtype=torch.float32)
-            last = i == net.num_stacks - 1
             score_pad = None if last else _Tensor(torch.zeros((N, h, h, 128), device=self.dev, dtype=BF16), None, h, h, 128)
             sc_b = self.conv(net.score[i], yf_buf, 256, score_pad, y_nchw=score, want_stats=False)
             scores.append(score)
@@ -351,25 +396,23 @@ class _Run:
                 fcu_b = self.conv(net.fc_[i], yf_buf, 256, t, residual=x.buf, want_stats=False)
                 xn = self.act(h, h, 256)
                 scu_b = self.conv(net.score_[i], score_pad.buf, 128, xn, residual=t.buf)
+                xn.bias_grads = [net.grad_view(net.fc_[i].bias), net.grad_view(net.score_[i].bias)]   # both see dL/dxn
             else:
                 fcu_b = scu_b = xn = None
-            stack_b.append((hg_b, res_b, fc_b, fcgn_b, sc_b, fcu_b, scu_b, x, h))
+            stack_b.append((hg_b, res_b, fc_b, fcgn_b, sc_b, fcu_b, scu_b, x, y, h))
             if not last:
                 x = xn
 
         def backward(grad_scores):
             dx_next = None            # gradient w.r.t. the input of the following stack
             for i in reversed(range(net.num_stacks)):
-                hg_b, res_b, fc_b, fcgn_b, sc_b, fcu_b, scu_b, xin, hh = stack_b[i]
+                hg_b, res_b, fc_b, fcgn_b, sc_b, fcu_b, scu_b, xin, yres, hh = stack_b[i]
                 g = grad_scores[i]
                 dscore = torch.zeros((N, hh, hh, 128), device=self.dev, dtype=BF16)
                 if g is not None:
                     ops.nchw_to_nhwc(g.contiguous().float(), N, K, hh * hh, 128, dscore)
                 dyf = None
                 if dx_next is not None:
-                    # bias gradients of fc_ and score_ see dx_next
-                    ops.colsum(dx_next, N, hh * hh, 256, net.grad_view(net.fc_[i].bias))
-                    net.grad_view(net.score_[i].bias).copy_(net.grad_view(net.fc_[i].bias))
                     dsp = scu_b(dx_next, 256)                       # [N,h,h,128] gradient of the padded score copy
                     tmp = torch.empty_like(dscore)
                     ops.add(dscore, dsp, N, hh * hh, 128, tmp)
@@ -381,17 +424,20 @@ class _Run:
                 dyf = sc_b(dscore, 128, dx_addend=dyf)
                 df = fcgn_b(dyf, colsum=net.grad_view(net.fc[i][0].bias))
                 dy = fc_b(df, 256)
+                self.cs_fallback(yres, dy)                          # a conv data-gradient: no fused column sum
                 dy = res_b(dy)
                 dxin = hg_b(dy)
                 if dx_next is not None:
                     tmp = torch.empty_like(dxin)
-                    ops.add(dxin, dx_next, N, hh * hh, 256, tmp)
+                    ops.add(dxin, dx_next, N, hh * hh, 256, tmp, colsum=self.cs(xin))
+                    self.cs_done(xin)
                     dxin = tmp
                 dx_next = dxin
             d = l3_b(dx_next)
             d = l2_b(d)
             dl1 = torch.empty_like(l1.buf)
-            ops.maxpool_bwd(d, l1.buf, N, H2, H2, 128, dl1)
+            ops.maxpool_bwd(d, l1.buf, N, H2, H2, 128, dl1, colsum=self.cs(l1))
+            self.cs_done(l1)
             dx0 = l1_b(dl1)
             dc1 = stem_gn_b(dx0)
             ops.stem_conv_wgrad(self.img, dc1, N, S, net.grad_view(net.conv1.weight), net.grad_view(net.conv1.bias))

@@ -101,7 +101,7 @@ def test_gn_relu_fwd_bwd(N, H, C, G):
     ops.gn_relu_fwd(xh, st, gamma.detach(), beta.detach(), N, H * H, C, G, y, st_out, 16)
     assert rel_err(nchw(y).cpu(), ref.detach().cpu()) < 1e-2
     assert rel_err(st_out.cpu(), stats_of(y, 16).cpu()) < 1e-3
-    red = torch.empty((N, G, 2), device=DEV)
+    red = ops.gn_relu_bwd_scratch(N, G, DEV)
     dg, db, cs = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     dx = torch.empty_like(xh)
     ops.gn_relu_bwd(nhwc(da), xh, st, gamma.detach(), beta.detach(), N, H * H, C, G, red, dg, db, dx, nhwc(add), cs)

@@ -70,7 +70,7 @@ def gn_case(H, C, G=16):
     us = timeit(lambda i: ops.gn_relu_fwd(xs[i % RING], st, gamma, beta, N, H * H, C, G, ys[i % RING]))
     byts = N * H * H * C * 2 * 2
     print('gn_relu_fwd C=%3d @%3d         : %8.1f us  %7.0f GB/s' % (C, H, us, byts / us * 1e-3), flush=True)
-    red = torch.empty(N, G, 2, device=DEV)
+    red = ops.gn_relu_bwd_scratch(N, G, DEV)
     dg, db, cs = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     us = timeit(lambda i: ops.gn_relu_bwd(das[i % RING], xs[i % RING], st, gamma, beta, N, H * H, C, G, red, dg, db, ys[i % RING], ads[i % RING], cs))
     byts = N * H * H * C * 2 * 4       # minimum traffic of a fused single pass: da, x, addend in, dx out
