@@ -187,6 +187,22 @@ int sh_step_combine(const void* g_mvproj, const void* g_pose3, const void* g_pri
                     const void* target_xyz4, const void* loss_mv3, const void* loss_pose3, const void* loss_prior3,
                     const void* sse2, int Ns, int M, int J, int hw, const float* weights8, float mean_scale, void* gxyz,
                     void* terms9, void* stream);
+/* ------------------------------------------------------------------------------------------------ stand-alone module entries
+ * What the fused step folds into larger kernels, exported one by one for the drop-in nn.Modules.
+ * sh_data_to_model_fwdbwd replaces DataToModelLoss.forward (mesh/render.py:123-142) and its backward: dms [N,H,W] mm
+ * (background > 99), joints [N,J,3], radii [J] -> loss[1], grad_joints [N,J,3] (upstream 1).  N <= 65535, J <= 64. */
+size_t sh_data_to_model_scratch_bytes(int N, int J);
+int sh_data_to_model_fwdbwd(const void* dms, const void* joints, const void* radii, int N, int J, int H, int W,
+                            void* loss, void* grad_joints, void* scratch, void* stream);
+/* OthographicalProjection.forward (mesh/pointTransformation.py:84-99; mode 1 = per-sample focal jitter rand_f [B], w := 1;
+ * mode 2 = K-matrix) and InverseOthographicalProjection.forward (:118-124; mode 3).  points, out float4 [B,Nv]. */
+int sh_ortho_project(const void* points, int B, int Nv, int mode, float cx, float cy, float fx, float fy,
+                     const void* rand_f, void* out, void* stream);
+/* RandScale.forward's matrix product (mesh/pointTransformation.py:144-148): out = diag(scales[b],1) * mats[b,m]. */
+int sh_rand_scale_apply(const void* mats, const void* scales, int B, int nmat, void* out, void* stream);
+/* torch.clamp(x, max=max_value) of DepthRasterizationFunction.forward (mesh/render.py:286); NaN propagates. */
+int sh_clamp_max(const void* x, long n, float max_value, void* y, void* stream);
+
 /* y = x * s on n fp32 elements: real_dms * depth_scale (network/engine.py:337), xyz / 100 (create_network_and_criterion.py:240). */
 int sh_scale(const void* x, float s, long n, void* y, void* stream);
 

@@ -145,10 +145,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// Sum `v[8]` (this thread's 8 channels c0..c0+7) over all threads of the block that own the same channels, into
+// dst[C] (+=), without shared-memory float atomics (those are CAS loops): shuffle over the row slots inside the warp, then
+// the warps take turns.  Must be called by every thread of the block.
+__device__ __forceinline__ void block_channel_sum(float* v, float* dst, int vecs, int c0) {
+    for (int o = vecs; o < 32; o <<= 1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool owner = vecs >= 32 || lane < vecs;
+    for (int wi = 0; wi < kBT / 32; ++wi) {
+        if (warp == wi && owner) {
+            float4* d = reinterpret_cast<float4*>(dst + c0);
+            float4 a = d[0], b = d[1];
+            a.x += v[0]; a.y += v[1]; a.z += v[2]; a.w += v[3];
+            b.x += v[4]; b.y += v[5]; b.z += v[6]; b.w += v[7];
+            d[0] = a; d[1] = b;
+        }
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ x,
@@ -161,8 +182,8 @@ __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16
     extern __shared__ __align__(128) uint8_t bwd_smem[];
     __shared__ float s_mr[32 * 2];
     __shared__ float s_red[32 * 2];
-    __shared__ float s_gb[2][256];
-    __shared__ float s_cs[256];
+    __shared__ __align__(16) float s_gb[2][256];
+    __shared__ __align__(16) float s_cs[256];
     __shared__ __align__(8) uint64_t s_bar[2];
     const int n = blockIdx.y;
     const int p0 = blockIdx.x * ppb;
@@ -236,23 +257,19 @@ __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16
                 db[e] += dy;
             }
         }
-        // per-group sums from the per-channel ones: A = sum gamma*dbeta_c, Bq = sum gamma*dgamma_c
-        float A[2] = {0.f, 0.f}, Bq[2] = {0.f, 0.f};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float ga = gamma[c0 + e];
-            const int h = (gs == 4) ? (e >> 2) : 0;
-            A[h] = fmaf(ga, db[e], A[h]);
-            Bq[h] = fmaf(ga, dg[e], Bq[h]);
+        block_channel_sum(dg, s_gb[0], vecs, c0);
+        block_channel_sum(db, s_gb[1], vecs, c0);
+    }
+    // per-group sums from the per-channel ones: A = sum gamma*dbeta_c, Bq = sum gamma*dgamma_c
+    if (threadIdx.x < G) {
+        float A = 0.f, Bq = 0.f;
+        for (int c = threadIdx.x * gs; c < (threadIdx.x + 1) * gs; ++c) {
+            const float ga = gamma[c];
+            A = fmaf(ga, s_gb[1][c], A);
+            Bq = fmaf(ga, s_gb[0][c], Bq);
         }
-        if (gs == 4) {
-            atomicAdd(&s_red[(c0 / 4) * 2], A[0]); atomicAdd(&s_red[(c0 / 4) * 2 + 1], Bq[0]);
-            atomicAdd(&s_red[(c0 / 4 + 1) * 2], A[1]); atomicAdd(&s_red[(c0 / 4 + 1) * 2 + 1], Bq[1]);
-        } else {
-            atomicAdd(&s_red[(c0 / gs) * 2], A[0]); atomicAdd(&s_red[(c0 / gs) * 2 + 1], Bq[0]);
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { atomicAdd(&s_gb[0][c0 + e], dg[e]); atomicAdd(&s_gb[1][c0 + e], db[e]); }
+        s_red[threadIdx.x * 2] = A;
+        s_red[threadIdx.x * 2 + 1] = Bq;
     }
     __syncthreads();
     if (gridDim.x > 1) {
@@ -265,8 +282,10 @@ __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16
     }
     for (int c = threadIdx.x; c < C; c += kBT) { atomicAdd(&dgamma[c], s_gb[0][c]); atomicAdd(&dbeta[c], s_gb[1][c]); }
     if (gridDim.x > 1) {
-        if (threadIdx.x == 0)
-            while (ld_acquire_u32(&counter[n]) < gridDim.x) __nanosleep(32);
+        if (threadIdx.x == 0) {
+            while (ld_relaxed_u32(&counter[n]) < gridDim.x) __nanosleep(20);
+            __threadfence();
+        }
         __syncthreads();
         if (threadIdx.x < G * 2) s_red[threadIdx.x] = __ldcg(&red[(size_t)n * G * 2 + threadIdx.x]);
         __syncthreads();
@@ -304,18 +323,16 @@ __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (colsum) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[c0 + e], cs[e]);
-    }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (uint32_t o = 0; o < bytes; o += 4096)
             bulk_s2g(reinterpret_cast<uint8_t*>(dx + goff) + o, s_da + o, min(4096u, bytes - o));
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    if (colsum)
+    if (colsum) {
+        block_channel_sum(cs, s_cs, vecs, c0);
         for (int c = threadIdx.x; c < C; c += kBT) atomicAdd(&colsum[c], s_cs[c]);
+    }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 

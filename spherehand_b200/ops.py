@@ -316,6 +316,39 @@ def step_combine(xyz, Ns, M, J, hw, weights8, gxyz, terms9, g_mvproj=None, g_pos
           _stream())
 
 
+def data_to_model_fwdbwd(dms, joints, radii):
+    N, H, W = dms.shape
+    J = joints.shape[1]
+    dev = dms.device
+    loss = torch.empty(1, device=dev, dtype=torch.float32)
+    grad = torch.empty((N, J, 3), device=dev, dtype=torch.float32)
+    scratch = torch.empty(_lib.lib().sh_data_to_model_scratch_bytes(N, J) // 4 + 4, device=dev, dtype=torch.float32)
+    _call('sh_data_to_model_fwdbwd', _chk(dms, name='dms'), _chk(joints, name='joints'), _chk(radii, name='radii'), N, J, H, W,
+          loss.data_ptr(), grad.data_ptr(), scratch.data_ptr(), _stream())
+    return loss, grad
+
+
+def ortho_project(points, mode, cam, rand_f=None):
+    B, Nv = points.shape[:2]
+    out = torch.empty_like(points)
+    _call('sh_ortho_project', _chk(points, name='points'), B, Nv, mode, float(cam[0]), float(cam[1]), float(cam[2]), float(cam[3]),
+          _opt(rand_f, name='rand_f'), out.data_ptr(), _stream())
+    return out
+
+
+def rand_scale_apply(mats, scales):
+    B, nmat = mats.shape[:2]
+    out = torch.empty_like(mats)
+    _call('sh_rand_scale_apply', _chk(mats, name='mats'), _chk(scales, name='scales'), B, nmat, out.data_ptr(), _stream())
+    return out
+
+
+def clamp_max(x, max_value):
+    out = torch.empty_like(x)
+    _call('sh_clamp_max', _chk(x, name='x'), x.numel(), float(max_value), out.data_ptr(), _stream())
+    return out
+
+
 def scale(x, s, out):
     _call('sh_scale', _chk(x, name='x'), float(s), x.numel(), _chk(out, name='out'), _stream())
     return out
