@@ -27,3 +27,19 @@ def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def mesh_dict(a):
+    """The reference's `mesh` dict (mesh/preprocess.py output: vertices, faces, bones[{offset_matrix, weight_vertexid,
+    weight_coeff, keypoint}]) rebuilt from the arrays of tests/golden/hand_model.npz."""
+    bones = []
+    for b in range(a['offset_mats'].shape[0]):
+        sel = a['weight_bone'] == b
+        bone = {'offset_matrix': np.asarray(a['offset_mats'][b], np.float64),
+                'weight_vertexid': a['weight_vertexid'][sel].tolist(), 'weight_coeff': a['weight_coeff'][sel].tolist()}
+        kp = [(np.asarray(a['keypoints'][k], np.float64), float(a['keypoint_radius'][k]))
+              for k in range(len(a['keypoint_bone'])) if a['keypoint_bone'][k] == b]
+        if kp:
+            bone['keypoint'] = kp
+        bones.append(bone)
+    return {'vertices': np.asarray(a['vertices']), 'faces': np.array(a['faces'], copy=True), 'bones': bones}

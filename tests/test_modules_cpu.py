@@ -1,0 +1,112 @@
+"""CPU-side checks of the drop-in module surfaces (no kernel runs): constructor arguments, registered buffers /
+state_dict keys the reference's checkpoints and callers rely on, host-side tables, and the no-CPU-fallback rule."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, mesh_dict
+from oracle import hourglass as oh, losses
+
+import spherehand_b200
+from spherehand_b200.mesh import bone_length, kinematicsTransformation as kt, multiview_utility as mv, pointTransformation as pt, render
+from spherehand_b200.network import create_network_and_criterion as cnc, pose_vae, util_modules
+from spherehand_b200.network.hourglass import create_hourglass_network
+
+
+def test_tables_match_the_reference_tables():
+    a, b = losses.collision_pairs()
+    col = render.CollisionLoss()
+    assert col.joint_1.tolist() == a.tolist() and col.joint_2.tolist() == b.tolist() and len(a) == 690
+    a, b, length = losses.bone_pairs()
+    assert bone_length.joint_1 == a.tolist() and bone_length.joint_2 == b.tolist()
+    assert np.allclose(bone_length.uniform_length, length) and len(length) == 35
+    bl = render.BoneLengthLoss()
+    assert torch.allclose(bl.min_length[0], (torch.tensor(length) * 0.8) ** 2) and torch.allclose(bl.max_length[0], (torch.tensor(length) * 1.05) ** 2)
+
+
+def test_module_surfaces_and_state_dict_keys(hand_model):
+    mesh = mesh_dict(hand_model)
+    radii = [float(r) for r in hand_model['keypoint_radius']]
+    assert set(render.BallRender(64, 48).state_dict()) == {'dist_weight', 'x_grid', 'y_grid'}
+    assert render.BallRender(64, 48).x_grid.shape == (48, 64)
+    d2m = render.DataToModelLoss(32, 32, mesh)
+    assert d2m.num_joints == 41 and d2m.radiuses.shape == (1, 1, 1, 41) and torch.allclose(d2m.radiuses.view(-1), torch.tensor(radii))
+    assert render.DataToModelLoss(32, 32, radii).num_joints == 41
+    with pytest.raises(TypeError):
+        render.DataToModelLoss(32, 32, np.asarray(radii))
+    mpl = mv.MutualProjectionLoss(64, mesh)
+    assert mpl.num_joints == 41 and 'mutual_projection.radiuses' in mpl.state_dict()
+    hb = render.HandBallPrimitiveRender(mesh['bones'], 64, 64)
+    assert hb.num_vertices == 41 and hb.radiuses.shape == (1, 41)
+    lbs = pt.LinearBlendSkinning(mesh['vertices'], [b['weight_coeff'] for b in mesh['bones']], [b['weight_vertexid'] for b in mesh['bones']])
+    assert lbs.num_vertices == 10144 and lbs.row_ptr[-1].item() == 25890 and lbs.wv.shape == (25890, 4)
+    with pytest.raises(AssertionError):
+        pt.LinearBlendSkinning(mesh['vertices'], [[1.0]], [[0], [1]])
+    faces = mesh['faces'].copy()
+    dr = render.DepthRender(mesh, 128)
+    assert np.array_equal(mesh['faces'], faces)                    # no in-place mutation of the caller's faces
+    assert dr.rasterizer.faces.dtype == torch.int64 and dr.rasterizer.faces.numel() == 3382 * 3
+    assert dr.rasterizer.faces.view(-1, 3)[:, 0].tolist() == faces[:, 1].tolist()      # right-hand winding swap (render.py:298-300)
+    assert dr.camera.k_mat.shape == (1, 4, 4) and dr.camera.k_mat[0, 0, 3] == 320
+    htm = kt.HandTransformationMat([b['offset_matrix'] for b in mesh['bones']])
+    assert htm.offset_mats.shape == (17, 4, 4)
+    with pytest.raises(AssertionError):
+        kt.HandTransformationMat([np.eye(4)] * 3)
+    hs = util_modules.HandSynthesizer(mesh, 64, 16, 1.0, 0.01)
+    assert hs.rand_scale.rand_scale == 0.1 and hs.depth_noiser.sigma_z == 0.05
+    rec = util_modules.RecoverXYZCoordinateFromHeatmap(16, 16, 0.01)
+    assert rec.depth_scale == 100.0 and set(rec.state_dict()) == {'u_grid', 'v_grid'}
+    vae = pose_vae.PoseVae(123, 32)
+    assert set(vae.state_dict()) == set(golden('pose_vae'))
+    with pytest.raises(ValueError):
+        pose_vae.PoseVae(60, 16)
+    net = cnc.HeatmapEstimationNetwork(32, 0.01, 41, 2, real_aug=False)
+    ref_keys = set('hg.' + k for k in oh.param_shapes(82, 2)) | {'xyz_recover.u_grid', 'xyz_recover.v_grid'}
+    assert set(net.state_dict()) == ref_keys                     # the keys of pretrained/*.pth (SURVEY.md §2.2 assets)
+
+    class Constant:
+        pass
+    Constant.mesh = mesh
+    crit = cnc.MultiTaskLoss(True, True, True, False, False, True, True, Constant(), image_size=128, heatmap_size=32)
+    assert crit.weights == {'synt_hm': 1e3, 'synt_pt': 1e-1, 'mv_consistency': 1e-3, 'mv_projection': 1, 'temporal_smooth': 1.0,
+                            'prior': 1e-2, 'hm_mean': 1e-2, 'domain': 0.0, 'collision': 1.0, 'bone_length': 1.0}
+    assert crit.prior_loss is None and crit.heatmap_size == 32
+    with pytest.raises(NotImplementedError):
+        cnc.MultiTaskLoss(True, True, True, True, False, True, True, Constant())
+
+
+def test_no_cpu_fallback_anywhere(hand_model):
+    """Every forward on CPU tensors raises (CHECK_CUDA of the reference shim, depth_rasterization_cuda.cpp:11-13): the
+    product path must never silently compute on the host."""
+    mesh = mesh_dict(hand_model)
+    with pytest.raises(RuntimeError):
+        spherehand_b200.depth_rasterization.forward(16, 16, torch.zeros(1, 2, 3, 3))
+    with pytest.raises(RuntimeError):
+        render.BallRender(16, 16)(torch.zeros(3, 3), torch.ones(3))
+    with pytest.raises(RuntimeError):
+        render.CollisionLoss()(torch.zeros(2, 3, 41, 3))
+    with pytest.raises(RuntimeError):
+        mv.MultiviewConsistencyLoss()(torch.eye(4).repeat(2, 3, 1, 1), torch.zeros(2, 3, 41, 3))
+    with pytest.raises(RuntimeError):
+        kt.HandTransformationMat([b['offset_matrix'] for b in mesh['bones']])(torch.zeros(2, 26))
+    with pytest.raises(RuntimeError):
+        create_hourglass_network(82, 1)(torch.zeros(1, 64, 64))
+    with pytest.raises(IndexError):
+        render.CollisionLoss()(torch.zeros(2, 40, 3))
+    with pytest.raises(TypeError):
+        spherehand_b200.depth_rasterization.forward(16, 16, np.zeros((1, 2, 3, 3), np.float32))
+
+
+def test_install_table():
+    import sys
+    before = set(sys.modules)
+    names = spherehand_b200.install()
+    try:
+        assert {'depth_rasterization', 'mesh.render', 'mesh.cuda_kernel', 'mesh.multiview_utility', 'mesh.kinematicsTransformation',
+                'mesh.pointTransformation', 'network.hourglass', 'network.create_network_and_criterion'} <= set(names)
+        import depth_rasterization
+        assert callable(depth_rasterization.forward)
+    finally:
+        for k in set(sys.modules) - before:
+            if k.split('.')[0] in ('mesh', 'network', 'depth_rasterization'):
+                sys.modules.pop(k, None)
