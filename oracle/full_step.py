@@ -47,10 +47,19 @@ def synthesize(tables, poses, scales, rand_f, noise, S, depth_scale=0.01):
 
 
 def loss_terms(sd, stacks, images, Ns, B, V, real, cams, inv_cams, uv_t, xyz_t, radii, vae_w, eps, is_mv=True,
-               depth_scale=0.01, weights=None, round_bf16=False, use=('proj', 'cons', 'prior', 'collision', 'bone')):
-    """Network + MultiTaskLoss -> (dict of weighted terms, list of projected_dms, list of real_xyz)."""
+               depth_scale=0.01, weights=None, round_bf16=False, use=('proj', 'cons', 'prior', 'collision', 'bone'),
+               term_scale=None):
+    """Network + MultiTaskLoss -> (dict of weighted terms, list of projected_dms, list of real_xyz).
+    term_scale(name) -> factor applied to each term as it is accumulated (names: the keys of the result plus
+    'pose_prior_recon' / 'pose_prior_kld' for the two halves of the prior); None = 1 (the reference)."""
     w = dict(WEIGHTS)
     w.update(weights or {})
+    if term_scale is not None:
+        ts = term_scale
+        w = dict(w)
+        w['synt_hm'] *= ts('synt_uv'); w['synt_pt'] *= ts('synt_d'); w['mv_projection'] *= ts('mv_projection')
+        w['mv_consistency'] *= ts('mv_consistency'); w['hm_mean'] *= ts('uv_hm_mean'); w['collision'] *= ts('collision')
+        w['bone_length'] *= ts('bone_length')
     J = 41
     outs, _ = oh.hourglass_forward(images, sd, stacks, round_bf16=round_bf16)
     t = {k: 0.0 for k in ('synt_uv', 'synt_d', 'mv_projection', 'mv_consistency', 'uv_hm_mean', 'pose_prior', 'collision',
@@ -71,7 +80,10 @@ def loss_terms(sd, stacks, images, Ns, B, V, real, cams, inv_cams, uv_t, xyz_t, 
             t['mv_consistency'] = t['mv_consistency'] + (w['mv_consistency'] if is_mv else 0.0) * ol.multiview_consistency(cams, joints)
         t['uv_hm_mean'] = t['uv_hm_mean'] + w['hm_mean'] * (o[Ns:, :J] ** 2).mean()
         if 'prior' in use:
-            t['pose_prior'] = t['pose_prior'] + w['prior'] * ol.vae_prior_loss((joints / 100.0).reshape(B * V, J * 3), vae_w, eps[si])
+            rec, kld = ol.vae_prior_loss((joints / 100.0).reshape(B * V, J * 3), vae_w, eps[si], parts=True)
+            if term_scale is not None:
+                rec, kld = rec * term_scale('pose_prior_recon'), kld * term_scale('pose_prior_kld')
+            t['pose_prior'] = t['pose_prior'] + w['prior'] * (rec + kld)
         if 'collision' in use:
             t['collision'] = t['collision'] + w['collision'] * ol.collision_loss(joints)
         if 'bone' in use:

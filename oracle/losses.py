@@ -145,8 +145,9 @@ def bone_length_loss(xyz):
     return F.relu(lo - sq).mean() + F.relu(sq - hi).mean()
 
 
-def vae_prior_loss(x, w, eps):
-    """pose_vae.py:81-89.  x [M,123] (already /100), w = dict of the state_dict tensors, eps [M,32]."""
+def vae_prior_loss(x, w, eps, parts=False):
+    """pose_vae.py:81-89.  x [M,123] (already /100), w = dict of the state_dict tensors, eps [M,32].
+    parts=True -> (reconstruction MSE [a batch MEAN], KLD [a batch SUM]) separately (data-parallel reduction rules)."""
     def lin(h, name):
         return F.linear(h, w[name + '.weight'], w[name + '.bias'])
 
@@ -162,6 +163,8 @@ def vae_prior_loss(x, w, eps):
     h = F.relu(gn(lin(h, 'decoder.3'), 'decoder.4'))
     recon = lin(h, 'decoder.6')
     kld = -0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp())
+    if parts:
+        return F.mse_loss(x, recon), kld
     return F.mse_loss(x, recon) + kld
 
 

@@ -16,7 +16,7 @@ not, so the summed gradient equals the single-GPU gradient at the global batch.
 """
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, parallel
 from .network.hourglass import HourglassNet
 
 LOSS_WEIGHTS = {          # MultiTaskLoss.weights, create_network_and_criterion.py:171-181
@@ -105,7 +105,7 @@ class SelfSupTrainStep:
         B, V, Ns, S, J, hm, N = self.B, self.V, self.Ns, self.S, self.J, self.hm, self.N
         M = B * V
         w = self.weights
-        ms = 1.0 / self.world_size
+        ms = parallel.mean_scale(self.world_size)
         # ---- synthetic branch (HandSynthesizer.forward): FK -> scale -> LBS -> project -> rasterise -> resize -> noise
         step, off, noff = _LATTICE[S]
         mats = ops.fk_fwd(self.poses, hand.offset_mats, hand.inv_offset_mats, self.scales)
@@ -162,9 +162,7 @@ class SelfSupTrainStep:
                           self.betas[0], self.betas[1], self.eps_adam, self.weight_decay)
 
     def _allreduce(self):
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.net._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+        parallel.allreduce_gradients(self.net._flat_grad, self.world_size, self.pg)
 
     def _capture(self, is_mv):
         """Warm up eagerly on a side stream (lazy CUDA init, cudaFuncSetAttribute, allocator), then capture."""
