@@ -110,3 +110,16 @@ def test_install_table():
         for k in set(sys.modules) - before:
             if k.split('.')[0] in ('mesh', 'network', 'depth_rasterization'):
                 sys.modules.pop(k, None)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """libspherehand_b200.so loads without a GPU and exports exactly what include/spherehand_b200.h declares."""
+    import subprocess
+    from spherehand_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 48 and 'sh_tri_raster_fwd' in protos and 'sh_conv_fwd' in protos
+    L = _lib.lib()                                         # binds every declared symbol (AttributeError if one is missing)
+    assert L.sh_abi_version() == 3 and L.sh_build_arch() == b'sm_100a'
+    exported = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    names = {l.split()[-1] for l in exported.splitlines() if ' T ' in l and l.split()[-1].startswith('sh_')}
+    assert names == set(protos), (names ^ set(protos))
