@@ -428,7 +428,10 @@ SH_EXPORT int sh_conv_fwd(const void* x, const void* w, const void* bias, const 
         }
         if (g.stages > kMaxStages) g.stages = kMaxStages;
         smem = (size_t)fixed + (size_t)g.stages * (kABytes + (g.b_resident ? 0 : b_tile)) + (g.b_resident ? resident : 0);
-        if (g.stages >= 3 || g.nstg == 2) break;
+        // Little's law: ~90 KB per SM must be in flight to saturate HBM; give up the third staging slot when the
+        // main-loop ring would otherwise hold less than 96 KB
+        const long inflight = (long)g.stages * (kABytes + (g.b_resident ? 0 : b_tile));
+        if (inflight >= 96 * 1024 || g.nstg == 2) break;
     }
     SH_REQUIRE(g.stages >= 2, "sh_conv_fwd: shared-memory plan failed");
     ConvPtrs p{(const float*)bias, (float*)y_nchw, (float*)stats};

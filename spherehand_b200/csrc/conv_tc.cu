@@ -56,6 +56,7 @@ int sh_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64
 namespace {
 
 constexpr int kThreads = 192;
+constexpr int kSmemMax = 232448;    // 227 KB opt-in maximum per CTA
 
 // ------------------------------------------------------------------------------------------------ wgrad
 // dW[tap][co][ci] += sum over pixels of dY[pix, co] * X[pix + tap, ci];  M = co (128), N = ci (BNW), K = pixels.
@@ -184,6 +185,139 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     if (warp == 1) tmem_dealloc(tmem_base, BNW);
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad, 1x1 layers
+// These layers are HBM-bound (2*HW*(Cin+Cout) bytes per image for 2*HW*Cin*Cout flops): every byte must be read ONCE.
+// One CTA owns the WHOLE [Cout <= 256] x [Cin <= 256] gradient: co_tiles (1 or 2) accumulators of 128 x cin_pad fp32 in
+// TMEM (<= 512 columns), so a pixel tile of dY and of X is fetched once chip-wide; K (= pixels) is split over one CTA
+// per SM with a deep TMA ring; the epilogue adds the partials with vector reductions (red.global.add.v4.f32).
+constexpr int kW1MaxStages = 8;
+struct Wgrad1Geom {
+    int N, H, W;
+    int bw, bh, bn;
+    int tiles_w, tiles_h, total_tiles;
+    int cin, cout;                 // real channel counts
+    int cin_pad;                   // N of the MMA (64, 128 or 256)
+    int co_tiles;                  // 1 or 2 accumulators of 128 rows
+    int stages, stage_bytes;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad1x1_kernel(const __grid_constant__ CUtensorMap tmDY,
+                                                               const __grid_constant__ CUtensorMap tmX,
+                                                               const Wgrad1Geom g, float* __restrict__ dw) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + g.stages * g.stage_bytes);
+    uint64_t* empty_bar = full_bar + kW1MaxStages;
+    uint64_t* accum_bar = empty_bar + kW1MaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (g.total_tiles + gridDim.x - 1) / gridDim.x;
+    const int tile_begin = blockIdx.x * per;
+    const int tile_end = min(tile_begin + per, g.total_tiles);
+    const int num_k = max(tile_end - tile_begin, 0);
+    const int a_bytes = g.co_tiles * 2 * kWPix * 128;
+    const uint32_t tmem_cols = (uint32_t)(g.co_tiles * g.cin_pad);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmDY);
+        tma_prefetch_desc(&tmX);
+        for (int s = 0; s < kW1MaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int k = 0; k < num_k; ++k) {
+                const int s = k % g.stages, it = k / g.stages;
+                mbar_wait(&empty_bar[s], (it & 1) ^ 1);
+                int tt = tile_begin + k;
+                const int tw = tt % g.tiles_w; tt /= g.tiles_w;
+                const int th = tt % g.tiles_h; tt /= g.tiles_h;
+                const int n0 = tt * g.bn, h0 = th * g.bh, w0 = tw * g.bw;
+                uint8_t* a_dst = smem + s * g.stage_bytes;
+                uint8_t* b_dst = a_dst + a_bytes;
+                mbar_expect_tx(&full_bar[s], (uint32_t)g.stage_bytes);
+                for (int c = 0; c < g.co_tiles * 2; ++c)
+                    tma_load_4d(a_dst + c * kWPix * 128, &tmDY, &full_bar[s], c * 64, w0, h0, n0);
+                for (int c = 0; c < g.cin_pad / 64; ++c)
+                    tma_load_4d(b_dst + c * kWPix * 128, &tmX, &full_bar[s], c * 64, w0, h0, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, g.cin_pad, 1, 1);
+            for (int k = 0; k < num_k; ++k) {
+                const int s = k % g.stages, it = k / g.stages;
+                mbar_wait(&full_bar[s], it & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * g.stage_bytes);
+                const uint32_t b_addr = a_addr + a_bytes;
+                for (int ct = 0; ct < g.co_tiles; ++ct) {
+#pragma unroll
+                    for (int kk = 0; kk < kWPix / 16; ++kk) {
+                        const uint64_t ad = umma_desc_mnmajor_sw128(a_addr + ct * 2 * kWPix * 128 + kk * 2048, kWPix * 128);
+                        const uint64_t bd = umma_desc_mnmajor_sw128(b_addr + kk * 2048, kWPix * 128);
+                        umma_bf16(tmem_base + (uint32_t)(ct * g.cin_pad), ad, bd, idesc, (k | kk) != 0);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        const int quad = warp & 3;
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        if (num_k > 0) {
+            const int vec = (g.cin % 4 == 0) ? 4 : ((g.cin % 2 == 0) ? 2 : 1);
+            for (int ct = 0; ct < g.co_tiles; ++ct) {
+                const int co = ct * 128 + quad * 32 + lane;
+#pragma unroll 1
+                for (int c0 = 0; c0 < g.cin_pad; c0 += 32) {
+                    if (c0 >= g.cin) break;                       // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ct * g.cin_pad + c0), v);
+                    tmem_ld_wait();
+                    if (co < g.cout) {
+                        float* dst = dw + (size_t)co * g.cin + c0;
+                        if (vec == 4) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                if (c0 + j < g.cin)
+                                    red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                               __uint_as_float(v[j + 3]));
+                        } else if (vec == 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2)
+                                if (c0 + j < g.cin) red_add_v2(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c0 + j < g.cin) atomicAdd(dst + j, __uint_as_float(v[j]));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 int make_act_tmap(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
@@ -206,6 +340,33 @@ SH_EXPORT int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, 
     SH_REQUIRE(x_C % 64 == 0 && dy_C % 64 == 0 && Cin >= 1 && Cin <= x_C && Cout >= 1 && Cout <= dy_C,
                "sh_conv_wgrad: channel counts must be multiples of 64 in memory");
     cudaStream_t st = (cudaStream_t)stream;
+    if (taps == 1 && x_C <= 256 && dy_C <= 256) {
+        Wgrad1Geom g1;
+        g1.N = N; g1.H = H; g1.W = W;
+        g1.bw = W < 16 ? W : 16;
+        g1.bh = H < kWPix / g1.bw ? H : kWPix / g1.bw;
+        g1.bn = kWPix / (g1.bw * g1.bh);
+        g1.tiles_w = W / g1.bw; g1.tiles_h = H / g1.bh;
+        g1.total_tiles = g1.tiles_w * g1.tiles_h * ((N + g1.bn - 1) / g1.bn);
+        g1.cin = Cin; g1.cout = Cout;
+        g1.cin_pad = x_C;
+        g1.co_tiles = (dy_C + 127) / 128;
+        g1.stage_bytes = (g1.co_tiles * 2 + g1.cin_pad / 64) * kWPix * 128;
+        g1.stages = (kSmemMax - 2048) / g1.stage_bytes;
+        if (g1.stages > kW1MaxStages) g1.stages = kW1MaxStages;
+        CUtensorMap tmDY, tmX;
+        int rc = make_act_tmap(&tmDY, dy, N, H, W, dy_C, g1.bw, g1.bh, g1.bn);
+        if (rc) return rc;
+        rc = make_act_tmap(&tmX, x, N, H, W, x_C, g1.bw, g1.bh, g1.bn);
+        if (rc) return rc;
+        static bool attr1 = false;
+        if (!attr1) { SH_CUDA(cudaFuncSetAttribute(wgrad1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)); attr1 = true; }
+        const int grid1 = g1.total_tiles < SH_NUM_SMS ? g1.total_tiles : SH_NUM_SMS;
+        const size_t smem1 = (size_t)g1.stages * g1.stage_bytes + 1024 + 512;
+        wgrad1x1_kernel<<<grid1, kThreads, smem1, st>>>(tmDY, tmX, g1, (float*)dw);
+        SH_CHECK_LAUNCH("wgrad1x1_kernel");
+        return SH_OK;
+    }
     WgradGeom g;
     g.N = N; g.H = H; g.W = W;
     g.bw = W < 16 ? W : 16;

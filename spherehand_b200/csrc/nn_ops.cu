@@ -582,87 +582,154 @@ __global__ void __launch_bounds__(kT) colsum_kernel(const __nv_bfloat16* __restr
 
 // ------------------------------------------------------------------------------------------------ stem: 5x5 stride-2 conv, Cin = 1
 // y[n,oh,ow,co] = b[co] + sum_{kh,kw} img[n, 2oh+kh-2, 2ow+kw-2] * w[co,kh,kw];  img fp32 [N,S,S]; y bf16 [N,S/2,S/2,64] + stats.
+// K = 25 is too thin for the tensor cores; register tiling on the CUDA cores instead: a block owns 2 output rows x 64
+// output columns of one image, the 7 x 132 input patch and the [tap][co] weights sit in shared memory, a thread computes
+// 4 adjacent output pixels x 8 channels (32 accumulators; per kernel row 11 input loads feed 160 FMAs).
+constexpr int kStemCols = 64;                 // output columns per block
+constexpr int kStemRows = 2;                  // output rows per block
+constexpr int kStemPatchW = 2 * kStemCols + 4;
 __global__ void __launch_bounds__(kT) stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ wgt,
-                                                           const float* __restrict__ bias, int S, int ppb, __nv_bfloat16* __restrict__ y,
+                                                           const float* __restrict__ bias, int S, __nv_bfloat16* __restrict__ y,
                                                            float* __restrict__ stats_out, int G_out) {
-    __shared__ float s_w[25 * 64];          // [tap][co]
-    __shared__ float s_b[64];
-    __shared__ float s_st[64];
-    const int n = blockIdx.y, O = S / 2, HW = O * O;
+    __shared__ __align__(16) float s_w[25 * 64];          // [tap][co]
+    __shared__ float s_in[(2 * kStemRows + 3) * kStemPatchW];
+    __shared__ float s_st[8][8];
+    const int n = blockIdx.z, O = S / 2;
+    const int oh0 = blockIdx.y * kStemRows, ow0 = blockIdx.x * kStemCols;
     for (int i = threadIdx.x; i < 25 * 64; i += kT) s_w[i] = wgt[(i % 64) * 25 + i / 64];
-    if (threadIdx.x < 64) { s_b[threadIdx.x] = bias[threadIdx.x]; s_st[threadIdx.x] = 0.f; }
+    for (int i = threadIdx.x; i < (2 * kStemRows + 3) * kStemPatchW; i += kT) {
+        const int r = i / kStemPatchW, c = i - r * kStemPatchW;
+        const int ih = 2 * oh0 - 2 + r, iw = 2 * ow0 - 2 + c;
+        s_in[i] = (ih >= 0 && ih < S && iw >= 0 && iw < S) ? __ldg(img + ((size_t)n * S + ih) * S + iw) : 0.f;
+    }
     __syncthreads();
-    const int cv = threadIdx.x % 8, r = threadIdx.x / 8;        // 8 channel vectors (64 ch), 32 pixel rows
+    const int cv = threadIdx.x & 7, q = threadIdx.x >> 3;            // 8 channel vectors x 32 pixel quads
     const int c0 = cv * 8;
-    float st[4] = {0.f, 0.f, 0.f, 0.f};
-    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
-    for (int pp = blockIdx.x * ppb + r; pp < p_end; pp += kT / 8) {
-        const int oh = pp / O, ow = pp % O;
-        bf8 acc;
+    const int lr = q / (kStemCols / 4), lc = (q % (kStemCols / 4)) * 4;   // local output row, first local output column
+    float acc[4][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc.v[e] = s_b[c0 + e];
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int kh = 0; kh < 5; ++kh) {
-            const int ih = 2 * oh + kh - 2;
-            if (ih < 0 || ih >= S) continue;
+        for (int e = 0; e < 8; ++e) acc[i][e] = bias[c0 + e];
 #pragma unroll
-            for (int kw = 0; kw < 5; ++kw) {
-                const int iw = 2 * ow + kw - 2;
-                if (iw < 0 || iw >= S) continue;
-                const float v = __ldg(img + ((size_t)n * S + ih) * S + iw);
-                const float* wp = s_w + (kh * 5 + kw) * 64 + c0;
+    for (int kh = 0; kh < 5; ++kh) {
+        float in[11];
+        const float* row = s_in + (2 * lr + kh) * kStemPatchW + 2 * lc;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc.v[e] += v * wp[e];
-            }
+        for (int j = 0; j < 11; ++j) in[j] = row[j];
+#pragma unroll
+        for (int kw = 0; kw < 5; ++kw) {
+            const float4 w0 = *reinterpret_cast<const float4*>(s_w + (kh * 5 + kw) * 64 + c0);
+            const float4 w1 = *reinterpret_cast<const float4*>(s_w + (kh * 5 + kw) * 64 + c0 + 4);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(in[2 * i + kw], wv[e], acc[i][e]);
         }
-        store8(y + ((size_t)n * HW + pp) * 64 + c0, acc);
-        if (stats_out) stats_accum(st, acc, 64 / G_out);
+    }
+    const int oh = oh0 + lr;
+    float st[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ow = ow0 + lc + i;
+        if (oh < O && ow < O) {
+            bf8 v;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v.v[e] = acc[i][e];
+            store8(y + (((size_t)n * O + oh) * O + ow) * 64 + c0, v);
+            if (stats_out) stats_accum(st, v, 64 / G_out);
+        }
     }
     if (stats_out) {
-        stats_flush(s_st, st, c0, 64 / G_out);
+        // thread-private sums -> block sums without shared float atomics.  gs = 64/G_out >= 8: a thread's 8 channels
+        // lie in ONE group (st[0], st[1]); lanes that share the group: same cv / (gs/8).
+        const int gs = 64 / G_out;
+        const int lanes_per_group = gs / 8;                           // consecutive cv values in one group (1, 2, 4 or 8)
+        float s1 = st[0], s2 = st[1];
+        for (int o = 1; o < lanes_per_group; o <<= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        for (int o = 8; o < 32; o <<= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane < 8 && (lane % lanes_per_group) == 0) {
+            s_st[warp][(lane / lanes_per_group) * 2 % 8] = s1;        // G_out <= 4 here (8 slots = 4 groups x 2)
+            s_st[warp][((lane / lanes_per_group) * 2 + 1) % 8] = s2;
+        }
         __syncthreads();
-        if (threadIdx.x < G_out * 2) atomicAdd(&stats_out[(size_t)n * G_out * 2 + threadIdx.x], s_st[threadIdx.x]);
+        if (threadIdx.x < G_out * 2) {
+            float t = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) t += s_st[w8][threadIdx.x];
+            atomicAdd(&stats_out[(size_t)n * G_out * 2 + threadIdx.x], t);
+        }
     }
 }
 
 // dW[co,kh,kw] = sum_{n,oh,ow} dy[n,oh,ow,co] * img[n,2oh+kh-2,2ow+kw-2];  db[co] = sum dy.   dw: fp32 [64,25], db: [64]
-__global__ void __launch_bounds__(kT) stem_conv_wgrad_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ dy,
-                                                             int S, int ppb, float* __restrict__ dw, float* __restrict__ db) {
+// Thread roles: 8 channel vectors x 5 kernel rows x 6 pixel slices = 240 threads; a thread keeps the 5 x 8 partial sums of
+// ITS kernel row (40 registers instead of 200), the five kernel-row roles of a pixel re-read dy through L1.
+constexpr int kStemWT = 240;
+__global__ void __launch_bounds__(kStemWT) stem_conv_wgrad_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ dy,
+                                                                  int S, int ppb, float* __restrict__ dw, float* __restrict__ db) {
     __shared__ float s_dw[26 * 64];         // [tap | bias][co]
     const int n = blockIdx.y, O = S / 2, HW = O * O;
-    for (int i = threadIdx.x; i < 26 * 64; i += kT) s_dw[i] = 0.f;
+    for (int i = threadIdx.x; i < 26 * 64; i += kStemWT) s_dw[i] = 0.f;
     __syncthreads();
-    const int cv = threadIdx.x % 8, r = threadIdx.x / 8;
+    const int cv = threadIdx.x & 7, kh = (threadIdx.x >> 3) % 5, sl = threadIdx.x / 40;
     const int c0 = cv * 8;
-    float acc[26][8];
+    float acc[5][8], bsum[8];
 #pragma unroll
-    for (int t = 0; t < 26; ++t)
+    for (int t = 0; t < 5; ++t)
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
-    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
-    for (int pp = blockIdx.x * ppb + r; pp < p_end; pp += kT / 8) {
-        const int oh = pp / O, ow = pp % O;
-        const bf8 g = load8(dy + ((size_t)n * HW + pp) * 64 + c0);
 #pragma unroll
-        for (int kh = 0; kh < 5; ++kh) {
+    for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
+    const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
+    constexpr int kU = 4;                                           // pixels in flight per thread: the dy loads come from HBM
+    for (int p0 = blockIdx.x * ppb + sl; p0 < p_end; p0 += 6 * kU) {
+        uint4 raw[kU];
+        float in[kU][5];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int pp = p0 + 6 * u;
+            raw[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (pp < p_end) raw[u] = *reinterpret_cast<const uint4*>(dy + ((size_t)n * HW + pp) * 64 + c0);
+            const int oh = pp / O, ow = pp - oh * O;
             const int ih = 2 * oh + kh - 2;
+            const bool row_ok = pp < p_end && ih >= 0 && ih < S;
+            const float* row = img + ((size_t)n * S + (row_ok ? ih : 0)) * S;
 #pragma unroll
             for (int kw = 0; kw < 5; ++kw) {
                 const int iw = 2 * ow + kw - 2;
-                const float v = (ih >= 0 && ih < S && iw >= 0 && iw < S) ? __ldg(img + ((size_t)n * S + ih) * S + iw) : 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[kh * 5 + kw][e] += v * g.v[e];
+                in[u][kw] = (row_ok && iw >= 0 && iw < S) ? __ldg(row + iw) : 0.f;
             }
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[25][e] += g.v[e];
+        for (int u = 0; u < kU; ++u) {
+            const uint32_t r[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+            float gv[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { gv[2 * e] = __uint_as_float(r[e] << 16); gv[2 * e + 1] = __uint_as_float(r[e] & 0xffff0000u); }
+#pragma unroll
+            for (int kw = 0; kw < 5; ++kw)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[kw][e] = fmaf(in[u][kw], gv[e], acc[kw][e]);
+            if (kh == 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bsum[e] += gv[e];
+            }
+        }
     }
+    // 6 slices share a (cv, kh) role: a handful of shared atomics per thread, once per block
 #pragma unroll
-    for (int t = 0; t < 26; ++t)
+    for (int kw = 0; kw < 5; ++kw)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(&s_dw[t * 64 + c0 + e], acc[t][e]);
+        for (int e = 0; e < 8; ++e) atomicAdd(&s_dw[(kh * 5 + kw) * 64 + c0 + e], acc[kw][e]);
+    if (kh == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&s_dw[25 * 64 + c0 + e], bsum[e]);
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < 25 * 64; i += kT) atomicAdd(&dw[(i % 64) * 25 + i / 64], s_dw[i]);
+    for (int i = threadIdx.x; i < 25 * 64; i += kStemWT) atomicAdd(&dw[(i % 64) * 25 + i / 64], s_dw[i]);
     if (threadIdx.x < 64) atomicAdd(&db[threadIdx.x], s_dw[25 * 64 + threadIdx.x]);
 }
 
@@ -907,11 +974,12 @@ SH_EXPORT int sh_stem_conv_fwd(const void* img, const void* w, const void* b, in
                                 void* stream) {
     SH_REQUIRE(img && w && b && y, "sh_stem_conv_fwd: null pointer");
     SH_REQUIRE(S % 2 == 0 && S >= 2, "sh_stem_conv_fwd: S must be even");
+    SH_REQUIRE(!stats_out || G_out == 1 || G_out == 2 || G_out == 4, "sh_stem_conv_fwd: G_out must be 1, 2 or 4");
+    SH_REQUIRE(N <= 65535, "sh_stem_conv_fwd: N > 65535");
     if (N == 0) return SH_OK;
-    const int HW = (S / 2) * (S / 2);
-    const int ppb = pick_ppb(HW, N, 32);
-    dim3 grid(sh_div_up(HW, ppb), N);
-    stem_conv_fwd_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const float*)img, (const float*)w, (const float*)b, S, ppb,
+    const int O = S / 2;
+    dim3 grid(sh_div_up(O, kStemCols), sh_div_up(O, kStemRows), N);
+    stem_conv_fwd_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const float*)img, (const float*)w, (const float*)b, S,
                                                                 (__nv_bfloat16*)y, (float*)stats_out, G_out);
     SH_CHECK_LAUNCH("stem_conv_fwd_kernel");
     return SH_OK;
@@ -922,10 +990,10 @@ SH_EXPORT int sh_stem_conv_wgrad(const void* img, const void* dy, int N, int S, 
     if (N == 0) return SH_OK;
     const int HW = (S / 2) * (S / 2);
     int ppb = HW;
-    while (ppb > 256 && (long)N * ((HW + ppb - 1) / ppb) < 2L * SH_NUM_SMS) ppb = (ppb + 1) / 2;
+    while (ppb > 384 && (long)N * ((HW + ppb - 1) / ppb) < 6L * SH_NUM_SMS) ppb = (ppb + 1) / 2;
     dim3 grid(sh_div_up(HW, ppb), N);
-    stem_conv_wgrad_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const float*)img, (const __nv_bfloat16*)dy, S, ppb, (float*)dw,
-                                                                  (float*)db);
+    stem_conv_wgrad_kernel<<<grid, kStemWT, 0, (cudaStream_t)stream>>>((const float*)img, (const __nv_bfloat16*)dy, S, ppb, (float*)dw,
+                                                                       (float*)db);
     SH_CHECK_LAUNCH("stem_conv_wgrad_kernel");
     return SH_OK;
 }
