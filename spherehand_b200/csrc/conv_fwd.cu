@@ -20,22 +20,25 @@
 //     thread owns one pixel row (tcgen05.ld 32x32b), adds bias + residual, rounds to bf16, accumulates the GroupNorm
 //     statistics of the ROUNDED values (butterfly warp reduction -> one atomic per value), writes the swizzled staging
 //     tile in place and one elected thread issues a TMA store; a ring of staging slots lets loads / math / stores overlap;
-//   * TWO epilogue warp-groups (one per accumulator buffer, i.e. alternate tiles): a single warp per scheduler cannot hide
-//     its own instruction latencies, two tiles' epilogues in flight can.
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue group 0 (even tiles of this CTA), warps 6..9 = epilogue group 1 (odd tiles).
+//   * FOUR epilogue warp-groups: the epilogue (TMEM load, bias, residual, rounding, statistics, staging) is what paces the
+//     HBM-bound 1x1 layers (ncu: the MMA and the TMA ring wait on it), and a warp cannot hide its own dependent-issue
+//     latencies; group (b, h) serves accumulator buffer b (alternate tiles) and the 64-channel chunks c = h, h+2, ...
+//     of it, 32 columns at a time (register budget of a 576-thread CTA), with its own staging slot.
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..17 = epilogue groups 0..3 (4 warps each, one TMEM lane quadrant per warp).
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int kBM = 128;           // pixels per tile = TMEM lanes
 constexpr int kBK = 64;            // channels per k-block = one 128-byte swizzle row
-constexpr int kThreads = 320;
+constexpr int kThreads = 576;
 constexpr int kMaxStages = 8;
-constexpr int kMaxStg = 3;         // epilogue staging slots per warp-group (2 or 3)
+constexpr int kGroups = 4;         // epilogue warp-groups, one 16 KB staging slot each
 constexpr int kABytes = kBM * kBK * 2;          // 16 KB
 constexpr int kStgBytes = kBM * 64 * 2;         // 16 KB: 128 pixels x 64 channels bf16
 constexpr int kSmemLimit = 232448;              // 227 KB opt-in maximum per CTA
+constexpr int kIdentBytes = 64 * 128;           // K-major 64x64 identity tile
 
 struct ConvGeom {
     int N, H, W;
@@ -51,7 +54,6 @@ struct ConvGeom {
     int b_resident;                // weights loaded once per CTA
     int has_res;                   // residual tile fetched by TMA
     int nchunks;                   // 64-channel output chunks the epilogue processes
-    int nstg;                      // staging slots per epilogue group (2 or 3)
 };
 
 struct ConvPtrs {
@@ -106,15 +108,16 @@ struct Bfly {
 };
 __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x / 2); }
 
-// Per-(sample, group) sum / sum of squares of one thread row's 64 rounded channels (packed bf16 pairs), reduced over
+// Per-(sample, group) sum / sum of squares of one thread row's 2*NW rounded channels (NW packed bf16 pairs), reduced over
 // the R lanes of the warp that belong to the same image; the lanes left owning a value issue one atomic each.
-template <int GS, int R>
-__device__ __forceinline__ void chunk_stats(const uint32_t (&packed)[32], bool row_ok, int lane, int cg, int cout,
-                                            float* __restrict__ stats_n) {
-    constexpr int V = 2 * (64 / GS);
+template <int GS, int R, int NW>
+__device__ __forceinline__ void row_stats(const uint32_t (&packed)[NW], bool row_ok, int lane, int cg, int cout,
+                                          float* __restrict__ stats_n) {
+    constexpr int NG = 2 * NW / GS;                        // groups in this slice
+    constexpr int V = 2 * NG;
     float vals[V];
 #pragma unroll
-    for (int gi = 0; gi < 64 / GS; ++gi) {
+    for (int gi = 0; gi < NG; ++gi) {
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < GS / 2; ++j) {
@@ -134,7 +137,7 @@ __device__ __forceinline__ void chunk_stats(const uint32_t (&packed)[32], bool r
     if ((lane & ((1 << plain) - 1)) == 0 && row_ok) {
 #pragma unroll
         for (int j = 0; j < left; ++j) {
-            const int idx = base + j;                       // = 2 * group-in-chunk + {0: sum, 1: sum of squares}
+            const int idx = base + j;                       // = 2 * group-in-slice + {0: sum, 1: sum of squares}
             if (cg + (idx >> 1) * GS < cout) atomicAdd(stats_n + (cg / GS) * 2 + idx, vals[j]);
         }
     }
@@ -153,15 +156,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
     const int stage_bytes = kABytes + (g.b_resident ? 0 : kBBytes);
     uint8_t* s_pipe = smem;
     uint8_t* s_bres = s_pipe + g.stages * stage_bytes;          // resident weights (size 0 when streamed)
-    uint8_t* s_stg = s_bres + (g.b_resident ? num_k * kBBytes : 0);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stg + 2 * g.nstg * kStgBytes);
+    uint8_t* s_ident = s_bres + (g.b_resident ? num_k * kBBytes : 0);   // 64x64 bf16 identity (residual add on the tensor core)
+    uint8_t* s_stg = s_ident + (g.has_res ? kIdentBytes : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stg + kGroups * kStgBytes);
     uint64_t* full_bar = bars;                                  // [kMaxStages]
     uint64_t* empty_bar = bars + kMaxStages;                    // [kMaxStages]
     uint64_t* b_full = bars + 2 * kMaxStages;                   // [1]
     uint64_t* acc_full = b_full + 1;                            // [2]
     uint64_t* acc_empty = acc_full + 2;                         // [2]
-    uint64_t* res_full = acc_empty + 2;                         // [2 groups][kMaxStg]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2 * kMaxStg);
+    uint64_t* res_full = acc_empty + 2;                         // [kGroups]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + kGroups);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);    // [256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -173,11 +177,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
         if (g.y_ld) tma_prefetch_desc(&tmOut);
         for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(b_full, 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
-        for (int s = 0; s < 2 * kMaxStg; ++s) mbar_init(&res_full[s], 1);
+        // a buffer is drained by one group (single-chunk layers) or by the two groups that split its chunks
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], g.nchunks >= 2 ? 256 : 128); }
+        for (int s = 0; s < kGroups; ++s) mbar_init(&res_full[s], 1);
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < 256; i += kThreads) s_bias[i] = (p.bias && i < g.cout) ? p.bias[i] : 0.f;
+    if (g.has_res) {
+        // I[n][k] = (n == k), K-major rows of 128 B with the 128-byte swizzle: 16-byte chunk j of row n sits at chunk j ^ (n & 7)
+        for (int i = threadIdx.x; i < kIdentBytes / 16; i += kThreads) {
+            const int n = i >> 3, j = i & 7;                    // row, logical chunk (channels 8j .. 8j+7)
+            uint32_t w4[4] = {0u, 0u, 0u, 0u};
+            if ((n >> 3) == j) w4[(n & 7) >> 1] = (n & 1) ? 0x3f800000u : 0x00003f80u;      // bf16 1.0 at element n % 8
+            *reinterpret_cast<uint4*>(s_ident + n * 128 + ((j ^ (n & 7)) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+        fence_async_smem();                                     // generic-proxy writes -> visible to tcgen05.mma
+    }
     if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
     tc_fence_before();
     __syncthreads();
@@ -207,6 +222,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
                     tma_load_4d(a_dst, &tmA, &full_bar[s], kb * kBK, t.w0 + dw, t.h0 + dh, t.n0);
                     if (!g.b_resident) tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], kb * kBK, tap * g.cout_pad);
                 }
+                if (g.has_res) {
+                    // the residual tile rides the same ring: one more "k-block" per 64 output channels, multiplied by I
+                    for (int c = 0; c < g.nchunks; ++c, ++it) {
+                        const int s = it % g.stages, ph = (it / g.stages) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_expect_tx(&full_bar[s], (uint32_t)kABytes);
+                        tma_load_4d(s_pipe + s * stage_bytes, &tmRes, &full_bar[s], c * 64, t.w0, t.h0, t.n0);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -233,12 +257,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
                         umma_bf16(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
                     umma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
                 }
+                if (g.has_res) {
+                    // D[:, 64c .. 64c+63] += R_c * I : bf16 residual values enter the fp32 accumulator exactly
+                    constexpr uint32_t idesc64 = umma_idesc_bf16(kBM, 64, 0, 0);
+                    const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(s_ident));
+                    for (int c = 0; c < g.nchunks; ++c, ++it) {
+                        const int s = it % g.stages, ph = (it / g.stages) & 1;
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(s_pipe + s * stage_bytes));
+#pragma unroll
+                        for (int kk = 0; kk < kBK / 16; ++kk)
+                            umma_bf16(d_tmem + (uint32_t)(c * 64), ad + 2 * kk, bd + 2 * kk, idesc64, 1u);
+                        umma_commit(&empty_bar[s]);
+                    }
+                }
                 umma_commit(&acc_full[buf]);                    // accumulator complete
             }
         }
     } else {
         // ===================== epilogue warp-groups =====================
-        const int grp = (warp - 2) >> 2;                        // accumulator buffer / tile parity this group serves
+        const int egrp = (warp - 2) >> 2;                       // 0..3
+        const int buf = egrp & 1;                               // accumulator buffer / tile parity this group serves
+        const int half = egrp >> 1;                             // which chunks of the tile: c = half, half + 2, ...
         const int quad = warp & 3;                              // TMEM lane quadrant this warp may read
         const int m = quad * 32 + lane;                         // tile row = pixel (box order: w fastest, then h, n)
         const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);   // issues this group's residual loads / output stores
@@ -247,105 +288,79 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
         const int gs = g.groups > 0 ? g.cout / g.groups : 64;   // channels per group
         const uint32_t row_off = (uint32_t)m * 128u;
         const uint32_t sw = (uint32_t)(m & 7);
-        uint8_t* my_stg = s_stg + grp * g.nstg * kStgBytes;
-        uint64_t* my_res = res_full + grp * kMaxStg;
-        const int first_tile = blockIdx.x + grp * gridDim.x, tile_step = 2 * gridDim.x;
-        int cc = 0;                                             // chunk counter of this group (staging ring position)
-        if (g.has_res && issuer && first_tile < g.num_tiles) {
-            const TileCoord t = tile_coord(g, first_tile);
-            mbar_expect_tx(&my_res[0], kStgBytes);
-            tma_load_4d(my_stg, &tmRes, &my_res[0], 0, t.w0, t.h0, t.n0);
-        }
+        uint8_t* stg = s_stg + egrp * kStgBytes;
+        const int first_tile = blockIdx.x + buf * gridDim.x, tile_step = 2 * gridDim.x;
+        const bool active = half == 0 || g.nchunks >= 2;
+        const bool use_slot = g.y_ld != 0;
         int lt = 0;                                             // tiles this group has processed
-        for (int tile = first_tile; tile < g.num_tiles; tile += tile_step, ++lt) {
+        for (int tile = first_tile; active && tile < g.num_tiles; tile += tile_step, ++lt) {
             const TileCoord t = tile_coord(g, tile);
             const int n = t.n0 + ln, h = t.h0 + lh, w = t.w0 + lw;
             const bool row_ok = n < g.N;
-            mbar_wait(&acc_full[grp], lt & 1);
+            mbar_wait(&acc_full[buf], lt & 1);
             tc_fence_after();
-            for (int c = 0; c < g.nchunks; ++c, ++cc) {
-                const int slot = cc % g.nstg;
-                uint8_t* stg = my_stg + slot * kStgBytes;
-                if (issuer) {
-                    // the store that last used slot (cc+1) % nstg (chunk cc+1-nstg) must have finished reading its smem
-                    if (g.nstg == 3) bulk_wait_read<1>(); else bulk_wait_read<0>();
-                    if (g.has_res) {
-                        int nc = c + 1, ntile = tile;
-                        if (nc == g.nchunks) { nc = 0; ntile = tile + tile_step; }
-                        if (ntile < g.num_tiles) {
-                            const TileCoord tn = tile_coord(g, ntile);
-                            const int ns = (cc + 1) % g.nstg;
-                            mbar_expect_tx(&my_res[ns], kStgBytes);
-                            tma_load_4d(my_stg + ns * kStgBytes, &tmRes, &my_res[ns], nc * 64, tn.w0, tn.h0, tn.n0);
-                        }
-                    }
-                }
-                uint32_t v[64];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * BN + c * 64);
-                tmem_ld32(taddr, v);
-                tmem_ld32(taddr + 32, v + 32);
-                if (g.has_res) mbar_wait(&my_res[slot], (cc / g.nstg) & 1);
-                tmem_ld_wait();
+            for (int c = half; c < g.nchunks; c += 2) {
                 const int cg = c * 64;                          // first channel of this chunk
-                uint32_t packed[32];
+                if (use_slot) {
+                    if (issuer) bulk_wait_read<0>();            // this group's previous store has finished reading the slot
+                    epi_bar(egrp);                              // ... and everyone knows
+                }
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {                // 32 accumulator columns at a time
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + cg + hh * 32), v);
+                    tmem_ld_wait();
+                    const int ch0 = cg + hh * 32;
+                    uint32_t packed[16];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {                   // 8 channels = one 16-byte smem chunk
-                    float f[8];
+                    for (int q = 0; q < 4; ++q) {               // 8 channels = one 16-byte smem chunk
+                        const uint32_t chunk16 = (uint32_t)(hh * 4 + q);
+                        float f[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + s_bias[cg + q * 8 + e];
-                    if (g.has_res) {
-                        const uint4 rv = *reinterpret_cast<const uint4*>(stg + row_off + (((uint32_t)q ^ sw) << 4));
-                        const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + s_bias[ch0 + q * 8 + e];
+                        if (p.y_nchw && row_ok) {
+                            const size_t hw = (size_t)g.H * g.W;
+                            float* o = p.y_nchw + ((size_t)n * g.cout + ch0 + q * 8) * hw + (size_t)h * g.W + w;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (ch0 + q * 8 + e < g.cout) o[(size_t)e * hw] = f[e];
+                        }
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            f[2 * e] += __uint_as_float(rr[e] << 16);
-                            f[2 * e + 1] += __uint_as_float(rr[e] & 0xffff0000u);
+                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                            packed[q * 4 + e] = *reinterpret_cast<const uint32_t*>(&b2);
+                        }
+                        if (g.y_ld)
+                            *reinterpret_cast<uint4*>(stg + row_off + ((chunk16 ^ sw) << 4)) =
+                                make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+                    }
+                    if (p.stats && ch0 < g.cout) {
+                        // statistics of the ROUNDED values; a group never straddles a 32-channel slice (gs | 32)
+                        float* sn = p.stats + (size_t)n * g.groups * 2;
+                        if (px_per_img >= 32) {
+                            if (gs == 4) row_stats<4, 32, 16>(packed, row_ok, lane, ch0, g.cout, sn);
+                            else if (gs == 8) row_stats<8, 32, 16>(packed, row_ok, lane, ch0, g.cout, sn);
+                            else if (gs == 16) row_stats<16, 32, 16>(packed, row_ok, lane, ch0, g.cout, sn);
+                            else row_stats<32, 32, 16>(packed, row_ok, lane, ch0, g.cout, sn);
+                        } else {                                // 4x4 images: a warp covers two images
+                            if (gs == 4) row_stats<4, 16, 16>(packed, row_ok, lane, ch0, g.cout, sn);
+                            else if (gs == 8) row_stats<8, 16, 16>(packed, row_ok, lane, ch0, g.cout, sn);
+                            else if (gs == 16) row_stats<16, 16, 16>(packed, row_ok, lane, ch0, g.cout, sn);
+                            else row_stats<32, 16, 16>(packed, row_ok, lane, ch0, g.cout, sn);
                         }
                     }
-                    if (p.y_nchw && row_ok) {
-                        const size_t hw = (size_t)g.H * g.W;
-                        float* o = p.y_nchw + ((size_t)n * g.cout + cg + q * 8) * hw + (size_t)h * g.W + w;
-#pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            if (cg + q * 8 + e < g.cout) o[(size_t)e * hw] = f[e];
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-                        packed[q * 4 + e] = *reinterpret_cast<const uint32_t*>(&b2);
-                    }
-                    if (g.y_ld)
-                        *reinterpret_cast<uint4*>(stg + row_off + (((uint32_t)q ^ sw) << 4)) =
-                            make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
                 }
                 if (g.y_ld) {
                     fence_async_smem();                         // generic-proxy writes -> visible to the TMA store
-                    epi_bar(grp);
+                    epi_bar(egrp);
                     if (issuer) {
                         tma_store_4d(&tmOut, stg, cg, t.w0, t.h0, t.n0);
                         bulk_commit();
                     }
-                } else if (g.has_res) {
-                    epi_bar(grp);                               // everyone done reading the residual slot
-                }
-                if (p.stats && cg < g.cout) {
-                    // statistics of the ROUNDED values; a group never straddles a 64-channel chunk (gs | 64)
-                    float* sn = p.stats + (size_t)n * g.groups * 2;
-                    if (px_per_img >= 32) {
-                        if (gs == 4) chunk_stats<4, 32>(packed, row_ok, lane, cg, g.cout, sn);
-                        else if (gs == 8) chunk_stats<8, 32>(packed, row_ok, lane, cg, g.cout, sn);
-                        else if (gs == 16) chunk_stats<16, 32>(packed, row_ok, lane, cg, g.cout, sn);
-                        else chunk_stats<32, 32>(packed, row_ok, lane, cg, g.cout, sn);
-                    } else {                                    // 4x4 images: a warp covers two images
-                        if (gs == 4) chunk_stats<4, 16>(packed, row_ok, lane, cg, g.cout, sn);
-                        else if (gs == 8) chunk_stats<8, 16>(packed, row_ok, lane, cg, g.cout, sn);
-                        else if (gs == 16) chunk_stats<16, 16>(packed, row_ok, lane, cg, g.cout, sn);
-                        else chunk_stats<32, 16>(packed, row_ok, lane, cg, g.cout, sn);
-                    }
                 }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[grp]);                       // 128 arrivals free the accumulator buffer
+            mbar_arrive(&acc_empty[buf]);                       // 128 arrivals per serving group free the accumulator buffer
         }
         if (issuer) bulk_wait_all();
     }
@@ -411,13 +426,13 @@ SH_EXPORT int sh_conv_fwd(const void* x, const void* w, const void* bias, const 
     g.has_res = residual ? 1 : 0;
     const int top = (y && y_ld > Cout) ? y_ld : Cout;
     g.nchunks = (top + 63) / 64;
-    // shared-memory plan: 2 epilogue groups x nstg staging slots, resident weights if they fit next to >= 2 A stages
+    // shared-memory plan: one 16 KB staging slot per epilogue group, resident weights if they fit next to >= 2 A stages
     const int num_k = taps * g.kblocks;
     const int b_tile = cout_pad * 128;
     const long resident = (long)num_k * b_tile;
     size_t smem = 0;
-    for (g.nstg = kMaxStg; g.nstg >= 2; --g.nstg) {
-        const int fixed = 1024 /*alignment*/ + 2 * g.nstg * kStgBytes + 2048 /*barriers + bias*/;
+    {
+        const int fixed = 1024 /*alignment*/ + kGroups * kStgBytes + 2048 /*barriers + bias*/ + (residual ? kIdentBytes : 0);
         const int avail = kSmemLimit - fixed;
         if (resident + 2 * kABytes <= avail) {
             g.b_resident = 1;
@@ -428,10 +443,6 @@ SH_EXPORT int sh_conv_fwd(const void* x, const void* w, const void* bias, const 
         }
         if (g.stages > kMaxStages) g.stages = kMaxStages;
         smem = (size_t)fixed + (size_t)g.stages * (kABytes + (g.b_resident ? 0 : b_tile)) + (g.b_resident ? resident : 0);
-        // Little's law: ~90 KB per SM must be in flight to saturate HBM; give up the third staging slot when the
-        // main-loop ring would otherwise hold less than 96 KB
-        const long inflight = (long)g.stages * (kABytes + (g.b_resident ? 0 : b_tile));
-        if (inflight >= 96 * 1024 || g.nstg == 2) break;
     }
     SH_REQUIRE(g.stages >= 2, "sh_conv_fwd: shared-memory plan failed");
     ConvPtrs p{(const float*)bias, (float*)y_nchw, (float*)stats};

@@ -23,7 +23,7 @@ def timeit(fn, reps=12):
     return e0.elapsed_time(e1) * 1e3 / reps
 
 
-def conv_case(H, Cin, Cout, taps, res, stats=True):
+def conv_case(H, Cin, Cout, taps, res, stats=os.environ.get('STATS', '1') == '1'):
     cout_pad = (Cout + 127) // 128 * 128 if Cout > 64 else 64
     xs = [torch.randn(N, H, H, Cin, device=DEV).to(BF16) for _ in range(RING)]
     rs = [torch.randn(N, H, H, Cout, device=DEV).to(BF16) for _ in range(RING)] if res else None
