@@ -61,6 +61,7 @@ def lib():
 
 
 PROFILE = None     # set to a list to record (entry name, args, start event, end event) per call (bench.py's kernel shares)
+NVTX = None        # set to a callable (entry name, args) -> range name | None to wrap calls in NVTX ranges (tools/profile_step.py)
 
 
 def call(name, *args):
@@ -70,7 +71,13 @@ def call(name, *args):
         import torch
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+    tag = NVTX(name, args) if NVTX is not None else None
+    if tag is not None:
+        import torch
+        torch.cuda.nvtx.range_push(tag)
     rc = getattr(lib(), name)(*args)
+    if tag is not None:
+        torch.cuda.nvtx.range_pop()
     if prof is not None:
         ev1.record()
         prof.append((name, args, ev0, ev1))

@@ -1,0 +1,66 @@
+"""ncu CSV logs (gpurun_out/) -> the summaries committed under profiles/.
+
+    python tools/summarise_ncu.py launches gpurun_out/launches.csv profiles/r1c_launches_summary.txt "<header note>"
+    python tools/summarise_ncu.py traffic gpurun_out/conv1x1.csv gpurun_out/conv3x3.csv profiles/conv_traffic.json "<source note>"
+"""
+import csv
+import json
+import sys
+from collections import defaultdict
+
+
+def rows_of(path):
+    lines = [l for l in open(path, errors='replace') if not l.startswith('==')]
+    rd = csv.reader(lines)
+    hdr = None
+    for r in rd:
+        if 'Kernel Name' in r:
+            hdr = r
+            break
+    iN, iM, iV = hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Value')
+    iI = hdr.index('ID')
+    out = defaultdict(dict)
+    names = {}
+    for r in rd:
+        if len(r) <= iV:
+            continue
+        names[r[iI]] = r[iN]
+        out[r[iI]][r[iM]] = float(r[iV].replace(',', ''))
+    return names, out
+
+
+def launches(path, dst, note):
+    names, vals = rows_of(path)
+    agg = defaultdict(lambda: [0, 0.0])
+    for i, n in names.items():
+        short = n.split('(')[0].replace('void ', '').replace('<unnamed>::', '')
+        agg[short][0] += 1
+        agg[short][1] += vals[i].get('gpu__time_duration.sum', 0.0) / 1e3      # ns -> us
+    tot = sum(v[1] for v in agg.values())
+    with open(dst, 'w') as f:
+        f.write('# %s\n# %d launches, total %.1f us (cold-cache, serialised: compare SHARES, not absolutes)\n' % (note, len(names), tot))
+        f.write('%-46s %5s %12s %7s %9s\n' % ('kernel', 'n', 'total_us', 'share', 'avg_us'))
+        for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write('%-46s %5d %12.1f %6.1f%% %9.1f\n' % (k[:46], n, us, 100 * us / tot, us / n))
+    print(open(dst).read())
+
+
+def traffic(p1, p3, dst, note):
+    out = {}
+    for key, path in (('1x1', p1), ('3x3', p3)):
+        names, vals = rows_of(path)
+        n = len(names)
+        rd = sum(v.get('dram__bytes_read.sum', 0.0) for v in vals.values())
+        wr = sum(v.get('dram__bytes_write.sum', 0.0) for v in vals.values())
+        us = sum(v.get('gpu__time_duration.sum', 0.0) for v in vals.values()) / 1e3
+        out[key] = dict(launches=n, dram_bytes_per_launch=(rd + wr) / max(n, 1), dram_read_bytes=rd, dram_write_bytes=wr,
+                        total_us_under_ncu=us, source=note)
+    json.dump(out, open(dst, 'w'), indent=1)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == '__main__':
+    if sys.argv[1] == 'launches':
+        launches(*sys.argv[2:5])
+    else:
+        traffic(*sys.argv[2:6])
