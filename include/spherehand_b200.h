@@ -129,6 +129,12 @@ int sh_conv_fwd(const void* x, const void* w, const void* bias, const void* resi
  * x bf16 [N,H,W,x_C]; x_C, dy_C multiples of 64; Cin <= x_C and Cout <= dy_C are the real channel counts. */
 int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout, int taps,
                   void* dw, void* stream);
+/* 3x3 weight gradient (W >= 16) accumulated into a [9][Cout][Cin] fp32 scratch (contiguous in Cin: vector reductions; zero it
+ * once per step), and the one-launch transposition of every layer's scratch into the reference layout:
+ * table int32 [n,4] (device) rows = (scratch offset, grad offset, Cout, Cin) in floats; grad[co][ci][kh][kw] += scratch[tap][co][ci]. */
+int sh_conv_wgrad3x3(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout,
+                     void* scratch, void* stream);
+int sh_unpack_wgrad_batch(const void* table, int n, const void* scratch, void* grad, void* stream);
 /* GroupNorm(G) + ReLU: y = relu(gn(x)); optional statistics of y for a following GroupNorm(G_out). */
 int sh_gn_relu_fwd(const void* x, const void* stats_in, const void* gamma, const void* beta, int N, int HW, int C,
                    int G, float eps, void* y, void* stats_out, int G_out, void* stream);

@@ -318,6 +318,151 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad1x1_kernel(const __grid_cons
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad, 3x3 layers
+// dW[kh][kw][co][ci] += sum_p dY[p][co] * X[p + (kh-1, kw-1)][ci].  With one TMA box per tap the smem fill traffic (32 KB
+// per 256 MMA cycles) is 3x what the L2 can feed.  Here a CTA owns ONE kernel row kh and keeps THREE accumulators
+// (kw = 0, 1, 2) in TMEM: per 64-pixel step it loads the dY tile once and ONE X box that is two pixels wider
+// ({64 ch, 18, 4}); the three taps are three views of that box -- the MN-major descriptor start shifted by kw rows
+// (tcgen05 swizzles on absolute smem address bits, tools/umma_probe.cu) -- so 34 KB feed 768 MMA cycles.
+// Output: fp32 partial sums added with red.global.add.v4 into a [tap][Cout][Cin] scratch (contiguous in ci), unpacked
+// into the reference layout [Cout][Cin][kh][kw] for all layers at once by sh_unpack_wgrad_batch.
+constexpr int kW3MaxStages = 6;
+constexpr int kW3XChunk = 18 * 4 * 128;        // 9216 B: one 64-channel chunk of the widened X box
+struct Wgrad3Geom {
+    int N, H, W;
+    int tiles_w, tiles_h, total_tiles;   // 64-pixel tiles (16 wide x 4 tall)
+    int cin, cout;
+    int ci_tiles, co_tiles;              // nmma-channel / 128-channel tiles
+    int nmma;                            // N of the MMA = input channels per CTA (64 or 128)
+    int ksplit, stages, stage_bytes;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad3x3_kernel(const __grid_constant__ CUtensorMap tmDY,
+                                                               const __grid_constant__ CUtensorMap tmX,
+                                                               const Wgrad3Geom g, float* __restrict__ scratch) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + g.stages * g.stage_bytes);
+    uint64_t* empty_bar = full_bar + kW3MaxStages;
+    uint64_t* accum_bar = empty_bar + kW3MaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x;                                      // ((kh * co_tiles + co_t) * ci_tiles + ci_t)
+    const int ci_t = t % g.ci_tiles; t /= g.ci_tiles;
+    const int co_t = t % g.co_tiles; t /= g.co_tiles;
+    const int kh = t;
+    const int per = (g.total_tiles + g.ksplit - 1) / g.ksplit;
+    const int tile_begin = blockIdx.y * per;
+    const int tile_end = min(tile_begin + per, g.total_tiles);
+    const int num_k = max(tile_end - tile_begin, 0);
+    constexpr int kABytes3 = 2 * kWPix * 128;               // dY: two 64-channel chunks of 64 pixels
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmDY);
+        tma_prefetch_desc(&tmX);
+        for (int s = 0; s < kW3MaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int k = 0; k < num_k; ++k) {
+                const int s = k % g.stages, it = k / g.stages;
+                mbar_wait(&empty_bar[s], (it & 1) ^ 1);
+                int tt = tile_begin + k;
+                const int tw = tt % g.tiles_w; tt /= g.tiles_w;
+                const int th = tt % g.tiles_h; tt /= g.tiles_h;
+                const int n0 = tt, h0 = th * 4, w0 = tw * 16;
+                uint8_t* a_dst = smem + s * g.stage_bytes;
+                uint8_t* b_dst = a_dst + kABytes3;
+                mbar_expect_tx(&full_bar[s], (uint32_t)g.stage_bytes);
+                for (int c = 0; c < 2; ++c)
+                    tma_load_4d(a_dst + c * kWPix * 128, &tmDY, &full_bar[s], co_t * 128 + c * 64, w0, h0, n0);
+                for (int c = 0; c < g.nmma / 64; ++c)        // X rows h0 + kh - 1 .., columns w0 - 1 .. w0 + 16 (zero fill = padding)
+                    tma_load_4d(b_dst + c * kW3XChunk, &tmX, &full_bar[s], ci_t * g.nmma + c * 64, w0 - 1, h0 + kh - 1, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, g.nmma, 1, 1);
+            for (int k = 0; k < num_k; ++k) {
+                const int s = k % g.stages, it = k / g.stages;
+                mbar_wait(&full_bar[s], it & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * g.stage_bytes);
+                const uint32_t b_addr = a_addr + kABytes3;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                    for (int hh = 0; hh < 4; ++hh) {         // K = 16 pixels = one image row of the tile
+                        const uint64_t ad = umma_desc_mnmajor_sw128(a_addr + hh * 2048, kWPix * 128);
+                        const uint64_t bd = umma_desc_mnmajor_sw128(b_addr + (uint32_t)(hh * 18 + kw) * 128u, kW3XChunk);
+                        umma_bf16(tmem_base + (uint32_t)(kw * g.nmma), ad, bd, idesc, (k | hh) != 0);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        const int quad = warp & 3;
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        if (num_k > 0) {
+            const int co = co_t * 128 + quad * 32 + lane;
+            const bool vec4 = (g.cin % 4) == 0;
+#pragma unroll 1
+            for (int kw = 0; kw < 3; ++kw) {
+                float* base = scratch + ((size_t)(kh * 3 + kw) * g.cout + co) * g.cin;
+#pragma unroll 1
+                for (int c0 = 0; c0 < g.nmma; c0 += 32) {
+                    const int ci0 = ci_t * g.nmma + c0;
+                    if (ci0 >= g.cin) break;                 // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kw * g.nmma + c0), v);
+                    tmem_ld_wait();
+                    if (co < g.cout) {
+                        if (vec4) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                if (ci0 + j < g.cin)
+                                    red_add_v4(base + ci0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                               __uint_as_float(v[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (ci0 + j < g.cin) atomicAdd(base + ci0 + j, __uint_as_float(v[j]));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// grad[co][ci][tap] += scratch[tap][co][ci] for every table row (scratch offset, grad offset, Cout, Cin), one launch
+__global__ void unpack_wgrad_batch_kernel(const int* __restrict__ table, const float* __restrict__ scratch, float* __restrict__ grad) {
+    const int* t = table + blockIdx.y * 4;
+    const float* src = scratch + t[0];
+    float* dst = grad + t[1];
+    const int cout = t[2], cin = t[3];
+    const long n = (long)cout * cin * 9;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % 9);
+        const long cc = i / 9;                               // co * cin + ci
+        dst[i] += src[(size_t)tap * cout * cin + cc];
+    }
+}
+
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 int make_act_tmap(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
@@ -399,5 +544,49 @@ SH_EXPORT int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, 
         wgrad_kernel<64><<<grid, kThreads, WgradSmem<64>::kTotal, st>>>(tmDY, tmX, g, (float*)dw);
     }
     SH_CHECK_LAUNCH("wgrad_kernel");
+    return SH_OK;
+}
+
+// 3x3 weight gradient into a [9][Cout][Cin] fp32 scratch (accumulated: zero it once per step), W >= 16, H >= 4.
+SH_EXPORT int sh_conv_wgrad3x3(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout,
+                               void* scratch, void* stream) {
+    SH_REQUIRE(dy && x && scratch, "sh_conv_wgrad3x3: null pointer");
+    SH_REQUIRE(N >= 1 && is_pow2(H) && is_pow2(W) && H >= 4 && W >= 16, "sh_conv_wgrad3x3: H >= 4, W >= 16, powers of two");
+    SH_REQUIRE(x_C % 64 == 0 && dy_C % 64 == 0 && Cin >= 1 && Cin <= x_C && Cout >= 1 && Cout <= dy_C,
+               "sh_conv_wgrad3x3: channel counts must be multiples of 64 in memory");
+    cudaStream_t st = (cudaStream_t)stream;
+    Wgrad3Geom g;
+    g.N = N; g.H = H; g.W = W;
+    g.tiles_w = W / 16; g.tiles_h = H / 4;
+    g.total_tiles = g.tiles_w * g.tiles_h * N;
+    g.cin = Cin; g.cout = Cout;
+    g.nmma = x_C % 128 == 0 ? 128 : 64;
+    g.ci_tiles = x_C / g.nmma; g.co_tiles = (dy_C + 127) / 128;
+    const int out_tiles = 3 * g.ci_tiles * g.co_tiles;
+    int ksplit = SH_NUM_SMS / out_tiles;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > g.total_tiles) ksplit = g.total_tiles;
+    g.ksplit = ksplit;
+    g.stage_bytes = 2 * kWPix * 128 + (g.nmma / 64) * kW3XChunk;      // 16 KB + 9 KB per 64 input channels: 1024-aligned
+    g.stages = kW3MaxStages;
+    CUtensorMap tmDY, tmX;
+    int rc = make_act_tmap(&tmDY, dy, N, H, W, dy_C, 16, 4, 1);
+    if (rc) return rc;
+    rc = make_act_tmap(&tmX, x, N, H, W, x_C, 18, 4, 1);
+    if (rc) return rc;
+    const size_t smem = (size_t)g.stages * g.stage_bytes + 1024 + 512;
+    static bool attr = false;
+    if (!attr) { SH_CUDA(cudaFuncSetAttribute(wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)); attr = true; }
+    wgrad3x3_kernel<<<dim3(out_tiles, ksplit), kThreads, smem, st>>>(tmDY, tmX, g, (float*)scratch);
+    SH_CHECK_LAUNCH("wgrad3x3_kernel");
+    return SH_OK;
+}
+
+// table int32 [n,4] (device): (scratch offset, grad offset, Cout, Cin) in floats; grad[co][ci][kh][kw] += scratch[tap][co][ci]
+SH_EXPORT int sh_unpack_wgrad_batch(const void* table, int n, const void* scratch, void* grad, void* stream) {
+    SH_REQUIRE(table && scratch && grad && n >= 0, "sh_unpack_wgrad_batch: bad arguments");
+    if (n == 0) return SH_OK;
+    unpack_wgrad_batch_kernel<<<dim3(32, n), 256, 0, (cudaStream_t)stream>>>((const int*)table, (const float*)scratch, (float*)grad);
+    SH_CHECK_LAUNCH("unpack_wgrad_batch_kernel");
     return SH_OK;
 }

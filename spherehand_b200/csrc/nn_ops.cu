@@ -55,13 +55,47 @@ __device__ __forceinline__ void stats_accum(float* st, const bf8& x, int gs) {
         for (int e = 0; e < 4; ++e) { st[0] += x.v[e]; st[1] += x.v[e] * x.v[e]; st[2] += x.v[4 + e]; st[3] += x.v[4 + e] * x.v[4 + e]; }
     }
 }
-__device__ __forceinline__ void stats_flush(float* s_st, const float* st, int c0, int gs) {
-    if (gs >= 8) {
-        atomicAdd(&s_st[(c0 / gs) * 2], st[0]);
-        atomicAdd(&s_st[(c0 / gs) * 2 + 1], st[1]);
-    } else {
-        atomicAdd(&s_st[(c0 / 4) * 2], st[0]); atomicAdd(&s_st[(c0 / 4) * 2 + 1], st[1]);
-        atomicAdd(&s_st[(c0 / 4 + 1) * 2], st[2]); atomicAdd(&s_st[(c0 / 4 + 1) * 2 + 1], st[3]);
+// Sum `v[8]` (this thread's 8 channels c0..c0+7) over all threads of the block that own the same channels, into
+// dst[C] (+=), without shared-memory float atomics (those compile to CAS loops): shuffle over the row slots inside the warp,
+// then the warps take turns.  Must be called by every thread of the NT-thread block; C/8 must divide 32.
+template <int NT>
+__device__ __forceinline__ void block_channel_sum(float* v, float* dst, int vecs, int c0) {
+    for (int o = vecs; o < 32; o <<= 1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool owner = vecs >= 32 || lane < vecs;
+    for (int wi = 0; wi < NT / 32; ++wi) {
+        if (warp == wi && owner) {
+            float4* d = reinterpret_cast<float4*>(dst + c0);
+            float4 a = d[0], b = d[1];
+            a.x += v[0]; a.y += v[1]; a.z += v[2]; a.w += v[3];
+            b.x += v[4]; b.y += v[5]; b.z += v[6]; b.w += v[7];
+            d[0] = a; d[1] = b;
+        }
+        __syncthreads();
+    }
+}
+// Block-wide reduction of the per-thread statistics of stats_accum and ONE global atomic per (group, moment):
+// s_tmp[256] must be zero on entry (and is left dirty); gs = channels per group of the consumer GroupNorm.
+template <int NT>
+__device__ __forceinline__ void stats_flush_block(const float* st, float* s_tmp, int vecs, int c0, int gs, int G_out,
+                                                  float* __restrict__ stats_out_n) {
+    float v[8] = {st[0], st[1], st[2], st[3], 0.f, 0.f, 0.f, 0.f};
+    block_channel_sum<NT>(v, s_tmp, vecs, c0);
+    if (threadIdx.x < G_out) {
+        const int g = threadIdx.x;
+        float s1 = 0.f, s2 = 0.f;
+        if (gs >= 8) {
+            const int lpg = gs / 8;                               // channel vectors per group
+            for (int cv = g * lpg; cv < (g + 1) * lpg; ++cv) { s1 += s_tmp[cv * 8]; s2 += s_tmp[cv * 8 + 1]; }
+        } else {
+            s1 = s_tmp[(g >> 1) * 8 + (g & 1) * 2];
+            s2 = s_tmp[(g >> 1) * 8 + (g & 1) * 2 + 1];
+        }
+        atomicAdd(stats_out_n + g * 2, s1);
+        atomicAdd(stats_out_n + g * 2 + 1, s2);
     }
 }
 
@@ -89,7 +123,7 @@ __global__ void __launch_bounds__(kT) gn_relu_fwd_kernel(const __nv_bfloat16* __
                                                          int HW, int C, int G, int ppb, float eps, __nv_bfloat16* __restrict__ y,
                                                          float* __restrict__ stats_out, int G_out) {
     __shared__ float s_mr[32 * 2];
-    __shared__ float s_st[32 * 2];
+    __shared__ __align__(16) float s_st[256];
     const int n = blockIdx.y;
     const int gs = C / G;
     const float cnt_inv = 1.f / ((float)HW * gs);
@@ -100,31 +134,45 @@ __global__ void __launch_bounds__(kT) gn_relu_fwd_kernel(const __nv_bfloat16* __
         s_mr[threadIdx.x * 2] = mean;
         s_mr[threadIdx.x * 2 + 1] = rsqrtf(var + eps);
     }
-    if (threadIdx.x < 64) s_st[threadIdx.x] = 0.f;
+    s_st[threadIdx.x] = 0.f;
     __syncthreads();
     const Walk w = make_walk(C);
     const int c0 = w.cv * 8;
-    float ga[8], be[8], mu[8], rs[8];
+    float ka[8], kb[8];                          // y = relu(x * ka + kb)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        ga[e] = gamma[c0 + e]; be[e] = beta[c0 + e];
-        mu[e] = s_mr[((c0 + e) / gs) * 2]; rs[e] = s_mr[((c0 + e) / gs) * 2 + 1];
+        const float mu = s_mr[((c0 + e) / gs) * 2], rs = s_mr[((c0 + e) / gs) * 2 + 1];
+        ka[e] = rs * gamma[c0 + e];
+        kb[e] = fmaf(-mu, ka[e], beta[c0 + e]);
     }
     float st[4] = {0.f, 0.f, 0.f, 0.f};
     const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
-    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
-        const size_t o = ((size_t)n * HW + pp) * C + c0;
-        bf8 v = load8(x + o);
+    constexpr int kU = 4;                        // independent 16-byte loads in flight per thread
+    const __nv_bfloat16* xb = x + (size_t)n * HW * C + c0;
+    __nv_bfloat16* yb = y + (size_t)n * HW * C + c0;
+    for (int p0 = blockIdx.x * ppb + w.r; p0 < p_end; p0 += w.rows * kU) {
+        uint4 raw[kU];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v.v[e] = fmaxf((v.v[e] - mu[e]) * rs[e] * ga[e] + be[e], 0.f);
-        store8(y + o, v);
-        if (stats_out) stats_accum(st, v, C / G_out);
+        for (int u = 0; u < kU; ++u) {
+            const int pp = p0 + u * w.rows;
+            raw[u] = pp < p_end ? *reinterpret_cast<const uint4*>(xb + (size_t)pp * C) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int pp = p0 + u * w.rows;
+            if (pp >= p_end) break;
+            const uint32_t r[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+            bf8 v;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                v.v[2 * e] = fmaxf(fmaf(__uint_as_float(r[e] << 16), ka[2 * e], kb[2 * e]), 0.f);
+                v.v[2 * e + 1] = fmaxf(fmaf(__uint_as_float(r[e] & 0xffff0000u), ka[2 * e + 1], kb[2 * e + 1]), 0.f);
+            }
+            store8(yb + (size_t)pp * C, v);
+            if (stats_out) stats_accum(st, v, C / G_out);
+        }
     }
-    if (stats_out) {
-        stats_flush(s_st, st, c0, C / G_out);
-        __syncthreads();
-        if (threadIdx.x < G_out * 2) atomicAdd(&stats_out[(size_t)n * G_out * 2 + threadIdx.x], s_st[threadIdx.x]);
-    }
+    if (stats_out) stats_flush_block<kT>(st, s_st, w.vecs, c0, C / G_out, G_out, stats_out + (size_t)n * G_out * 2);
 }
 
 // Backward, ONE pass over HBM: a block stages its contiguous [ppb pixels x C] slab of x, da (and the addend) in shared
@@ -150,28 +198,6 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// Sum `v[8]` (this thread's 8 channels c0..c0+7) over all threads of the block that own the same channels, into
-// dst[C] (+=), without shared-memory float atomics (those are CAS loops): shuffle over the row slots inside the warp, then
-// the warps take turns.  Must be called by every thread of the block.
-__device__ __forceinline__ void block_channel_sum(float* v, float* dst, int vecs, int c0) {
-    for (int o = vecs; o < 32; o <<= 1) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool owner = vecs >= 32 || lane < vecs;
-    for (int wi = 0; wi < kBT / 32; ++wi) {
-        if (warp == wi && owner) {
-            float4* d = reinterpret_cast<float4*>(dst + c0);
-            float4 a = d[0], b = d[1];
-            a.x += v[0]; a.y += v[1]; a.z += v[2]; a.w += v[3];
-            b.x += v[4]; b.y += v[5]; b.z += v[6]; b.w += v[7];
-            d[0] = a; d[1] = b;
-        }
-        __syncthreads();
-    }
-}
-
 __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ x,
                                                              const float* __restrict__ stats_in, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const __nv_bfloat16* __restrict__ addend,
@@ -257,8 +283,8 @@ __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16
                 db[e] += dy;
             }
         }
-        block_channel_sum(dg, s_gb[0], vecs, c0);
-        block_channel_sum(db, s_gb[1], vecs, c0);
+        block_channel_sum<kBT>(dg, s_gb[0], vecs, c0);
+        block_channel_sum<kBT>(db, s_gb[1], vecs, c0);
     }
     // per-group sums from the per-channel ones: A = sum gamma*dbeta_c, Bq = sum gamma*dgamma_c
     if (threadIdx.x < G) {
@@ -330,7 +356,7 @@ __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     if (colsum) {
-        block_channel_sum(cs, s_cs, vecs, c0);
+        block_channel_sum<kBT>(cs, s_cs, vecs, c0);
         for (int c = threadIdx.x; c < C; c += kBT) atomicAdd(&colsum[c], s_cs[c]);
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -340,9 +366,9 @@ __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16
 // y[n,h,w,:] = max over the 2x2 window of x; statistics of y; x is [N,2H,2W,C].
 __global__ void __launch_bounds__(kT) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int H, int W, int C, int ppb,
                                                          __nv_bfloat16* __restrict__ y, float* __restrict__ stats_out, int G_out) {
-    __shared__ float s_st[64];
+    __shared__ __align__(16) float s_st[256];
     const int n = blockIdx.y, HW = H * W;
-    if (threadIdx.x < 64) s_st[threadIdx.x] = 0.f;
+    s_st[threadIdx.x] = 0.f;
     __syncthreads();
     const Walk w = make_walk(C);
     const int c0 = w.cv * 8;
@@ -358,11 +384,7 @@ __global__ void __launch_bounds__(kT) maxpool_fwd_kernel(const __nv_bfloat16* __
         store8(y + ((size_t)n * HW + pp) * C + c0, r);
         if (stats_out) stats_accum(st, r, C / G_out);
     }
-    if (stats_out) {
-        stats_flush(s_st, st, c0, C / G_out);
-        __syncthreads();
-        if (threadIdx.x < G_out * 2) atomicAdd(&stats_out[(size_t)n * G_out * 2 + threadIdx.x], s_st[threadIdx.x]);
-    }
+    if (stats_out) stats_flush_block<kT>(st, s_st, w.vecs, c0, C / G_out, G_out, stats_out + (size_t)n * G_out * 2);
 }
 
 // dx[n,2h+i,2w+j,:] (+)= dy[n,h,w,:] for the FIRST maximal element of the window in (0,0),(0,1),(1,0),(1,1) order
@@ -371,7 +393,7 @@ __global__ void __launch_bounds__(kT) maxpool_fwd_kernel(const __nv_bfloat16* __
 __global__ void __launch_bounds__(kT) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                          const __nv_bfloat16* __restrict__ addend, int H, int W, int C, int ppb,
                                                          __nv_bfloat16* __restrict__ dx, float* __restrict__ colsum) {
-    __shared__ float s_cs[256];
+    __shared__ __align__(16) float s_cs[256];
     const int n = blockIdx.y, HW = H * W;
     if (threadIdx.x < 256) s_cs[threadIdx.x] = 0.f;
     __syncthreads();
@@ -414,9 +436,7 @@ __global__ void __launch_bounds__(kT) maxpool_bwd_kernel(const __nv_bfloat16* __
         }
     }
     if (colsum) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[c0 + e], cs[e]);
-        __syncthreads();
+        block_channel_sum<kT>(cs, s_cs, w.vecs, c0);
         for (int c = threadIdx.x; c < C; c += kT) atomicAdd(&colsum[c], s_cs[c]);
     }
 }
@@ -433,9 +453,9 @@ __device__ __forceinline__ void up_taps(int d, int n_src, int& i0, int& i1, floa
 __global__ void __launch_bounds__(kT) upsample_add_fwd_kernel(const __nv_bfloat16* __restrict__ up1, const __nv_bfloat16* __restrict__ low,
                                                               int h, int w_, int C, int ppb, __nv_bfloat16* __restrict__ y,
                                                               float* __restrict__ stats_out, int G_out) {
-    __shared__ float s_st[64];
+    __shared__ __align__(16) float s_st[256];
     const int n = blockIdx.y, H = 2 * h, W = 2 * w_, HW = H * W;
-    if (threadIdx.x < 64) s_st[threadIdx.x] = 0.f;
+    s_st[threadIdx.x] = 0.f;
     __syncthreads();
     const Walk w = make_walk(C);
     const int c0 = w.cv * 8;
@@ -457,17 +477,13 @@ __global__ void __launch_bounds__(kT) upsample_add_fwd_kernel(const __nv_bfloat1
         store8(y + ((size_t)n * HW + pp) * C + c0, r);
         if (stats_out) stats_accum(st, r, C / G_out);
     }
-    if (stats_out) {
-        stats_flush(s_st, st, c0, C / G_out);
-        __syncthreads();
-        if (threadIdx.x < G_out * 2) atomicAdd(&stats_out[(size_t)n * G_out * 2 + threadIdx.x], s_st[threadIdx.x]);
-    }
+    if (stats_out) stats_flush_block<kT>(st, s_st, w.vecs, c0, C / G_out, G_out, stats_out + (size_t)n * G_out * 2);
 }
 
 // dlow[n,i,j,:] = sum over the (up to 4x4) fine pixels that read (i,j) of weight * dy  (transpose of the above), + column sum
 __global__ void __launch_bounds__(kT) upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int h, int w_, int C, int ppb,
                                                           __nv_bfloat16* __restrict__ dlow, float* __restrict__ colsum) {
-    __shared__ float s_cs[256];
+    __shared__ __align__(16) float s_cs[256];
     const int n = blockIdx.y, hw = h * w_, H = 2 * h, W = 2 * w_;
     if (threadIdx.x < 256) s_cs[threadIdx.x] = 0.f;
     __syncthreads();
@@ -504,9 +520,7 @@ __global__ void __launch_bounds__(kT) upsample_bwd_kernel(const __nv_bfloat16* _
         }
     }
     if (colsum) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[c0 + e], cs[e]);
-        __syncthreads();
+        block_channel_sum<kT>(cs, s_cs, w.vecs, c0);
         for (int c = threadIdx.x; c < C; c += kT) atomicAdd(&colsum[c], s_cs[c]);
     }
 }
@@ -515,11 +529,11 @@ __global__ void __launch_bounds__(kT) upsample_bwd_kernel(const __nv_bfloat16* _
 __global__ void __launch_bounds__(kT) add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                                  const __nv_bfloat16* __restrict__ c, int HW, int C, int ppb, __nv_bfloat16* __restrict__ y,
                                                  float* __restrict__ stats_out, int G_out, float* __restrict__ colsum) {
-    __shared__ float s_st[64];
-    __shared__ float s_cs[256];
+    __shared__ __align__(16) float s_st[256];
+    __shared__ __align__(16) float s_cs[256];
     const int n = blockIdx.y;
-    if (threadIdx.x < 64) s_st[threadIdx.x] = 0.f;
-    if (threadIdx.x < 256) s_cs[threadIdx.x] = 0.f;
+    s_st[threadIdx.x] = 0.f;
+    s_cs[threadIdx.x] = 0.f;
     __syncthreads();
     const Walk w = make_walk(C);
     const int c0 = w.cv * 8;
@@ -546,20 +560,16 @@ __global__ void __launch_bounds__(kT) add_kernel(const __nv_bfloat16* __restrict
             for (int e = 0; e < 8; ++e) cs[e] += r.v[e];
         }
     }
-    if (stats_out) stats_flush(s_st, st, c0, C / G_out);
-    __syncthreads();
-    if (stats_out && threadIdx.x < G_out * 2) atomicAdd(&stats_out[(size_t)n * G_out * 2 + threadIdx.x], s_st[threadIdx.x]);
+    if (stats_out) stats_flush_block<kT>(st, s_st, w.vecs, c0, C / G_out, G_out, stats_out + (size_t)n * G_out * 2);
     if (colsum) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[c0 + e], cs[e]);
-        __syncthreads();
+        block_channel_sum<kT>(cs, s_cs, w.vecs, c0);
         for (int ch = threadIdx.x; ch < C; ch += kT) atomicAdd(&colsum[ch], s_cs[ch]);
     }
 }
 
 // column sum of a bf16 NHWC tensor (bias gradient when no producer kernel could fuse it)
 __global__ void __launch_bounds__(kT) colsum_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int ppb, float* __restrict__ colsum) {
-    __shared__ float s_cs[256];
+    __shared__ __align__(16) float s_cs[256];
     const int n = blockIdx.y;
     if (threadIdx.x < 256) s_cs[threadIdx.x] = 0.f;
     __syncthreads();
@@ -574,9 +584,7 @@ __global__ void __launch_bounds__(kT) colsum_kernel(const __nv_bfloat16* __restr
 #pragma unroll
         for (int e = 0; e < 8; ++e) cs[e] += r.v[e];
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[c0 + e], cs[e]);
-    __syncthreads();
+    block_channel_sum<kT>(cs, s_cs, w.vecs, c0);
     for (int ch = threadIdx.x; ch < C; ch += kT) atomicAdd(&colsum[ch], s_cs[ch]);
 }
 
@@ -665,70 +673,69 @@ __global__ void __launch_bounds__(kT) stem_conv_fwd_kernel(const float* __restri
 }
 
 // dW[co,kh,kw] = sum_{n,oh,ow} dy[n,oh,ow,co] * img[n,2oh+kh-2,2ow+kw-2];  db[co] = sum dy.   dw: fp32 [64,25], db: [64]
-// Thread roles: 8 channel vectors x 5 kernel rows x 6 pixel slices = 240 threads; a thread keeps the 5 x 8 partial sums of
-// ITS kernel row (40 registers instead of 200), the five kernel-row roles of a pixel re-read dy through L1.
-constexpr int kStemWT = 240;
+// One warp walks a stream of output pixels; lane l owns channels 2l, 2l+1 (the 128-byte dy row of a pixel is one coalesced
+// load) and keeps 25 x 2 partial sums; the 25 image taps of a pixel are warp-uniform loads.  ~85 instructions per pixel per
+// warp for 1600 MACs (the role-split version spent 275 on index arithmetic).  S/2 must be a power of two.
+constexpr int kStemWT = 256;
 __global__ void __launch_bounds__(kStemWT) stem_conv_wgrad_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ dy,
-                                                                  int S, int ppb, float* __restrict__ dw, float* __restrict__ db) {
+                                                                  int S, int log2O, int ppb, float* __restrict__ dw, float* __restrict__ db) {
     __shared__ float s_dw[26 * 64];         // [tap | bias][co]
     const int n = blockIdx.y, O = S / 2, HW = O * O;
     for (int i = threadIdx.x; i < 26 * 64; i += kStemWT) s_dw[i] = 0.f;
     __syncthreads();
-    const int cv = threadIdx.x & 7, kh = (threadIdx.x >> 3) % 5, sl = threadIdx.x / 40;
-    const int c0 = cv * 8;
-    float acc[5][8], bsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[25][2], bsum[2] = {0.f, 0.f};
 #pragma unroll
-    for (int t = 0; t < 5; ++t)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
+    for (int t = 0; t < 25; ++t) { acc[t][0] = 0.f; acc[t][1] = 0.f; }
     const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
-    constexpr int kU = 4;                                           // pixels in flight per thread: the dy loads come from HBM
-    for (int p0 = blockIdx.x * ppb + sl; p0 < p_end; p0 += 6 * kU) {
-        uint4 raw[kU];
-        float in[kU][5];
+    const float* im = img + (size_t)n * S * S;
+    const uint32_t* dyw = reinterpret_cast<const uint32_t*>(dy + (size_t)n * HW * 64) + lane;
+    constexpr int kU = 2;                   // pixels in flight per warp
+    for (int p0 = blockIdx.x * ppb + warp * kU; p0 < p_end; p0 += (kStemWT / 32) * kU) {
+        uint32_t raw[kU];
+        float in[kU][25];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const int pp = p0 + 6 * u;
-            raw[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (pp < p_end) raw[u] = *reinterpret_cast<const uint4*>(dy + ((size_t)n * HW + pp) * 64 + c0);
-            const int oh = pp / O, ow = pp - oh * O;
-            const int ih = 2 * oh + kh - 2;
-            const bool row_ok = pp < p_end && ih >= 0 && ih < S;
-            const float* row = img + ((size_t)n * S + (row_ok ? ih : 0)) * S;
+            const int pp = p0 + u;
+            const bool ok = pp < p_end;
+            raw[u] = ok ? __ldg(dyw + (size_t)pp * 32) : 0u;
+            const int oh = pp >> log2O, ow = pp & (O - 1);
 #pragma unroll
-            for (int kw = 0; kw < 5; ++kw) {
-                const int iw = 2 * ow + kw - 2;
-                in[u][kw] = (row_ok && iw >= 0 && iw < S) ? __ldg(row + iw) : 0.f;
+            for (int kh = 0; kh < 5; ++kh) {
+                const int ih = 2 * oh + kh - 2;
+                const bool rok = ok && ih >= 0 && ih < S;
+#pragma unroll
+                for (int kw = 0; kw < 5; ++kw) {
+                    const int iw = 2 * ow + kw - 2;
+                    in[u][kh * 5 + kw] = (rok && iw >= 0 && iw < S) ? __ldg(im + ih * S + iw) : 0.f;
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const uint32_t r[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
-            float gv[8];
+            const float g0 = __uint_as_float(raw[u] << 16), g1 = __uint_as_float(raw[u] & 0xffff0000u);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { gv[2 * e] = __uint_as_float(r[e] << 16); gv[2 * e + 1] = __uint_as_float(r[e] & 0xffff0000u); }
-#pragma unroll
-            for (int kw = 0; kw < 5; ++kw)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[kw][e] = fmaf(in[u][kw], gv[e], acc[kw][e]);
-            if (kh == 0) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) bsum[e] += gv[e];
+            for (int t = 0; t < 25; ++t) {
+                acc[t][0] = fmaf(in[u][t], g0, acc[t][0]);
+                acc[t][1] = fmaf(in[u][t], g1, acc[t][1]);
             }
+            bsum[0] += g0;
+            bsum[1] += g1;
         }
     }
-    // 6 slices share a (cv, kh) role: a handful of shared atomics per thread, once per block
+    // block reduction over the 8 warps: the warps take turns on the shared table (no shared float atomics)
+    for (int wi = 0; wi < kStemWT / 32; ++wi) {
+        if (warp == wi) {
 #pragma unroll
-    for (int kw = 0; kw < 5; ++kw)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(&s_dw[(kh * 5 + kw) * 64 + c0 + e], acc[kw][e]);
-    if (kh == 0) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(&s_dw[25 * 64 + c0 + e], bsum[e]);
+            for (int t = 0; t < 25; ++t) {
+                s_dw[t * 64 + 2 * lane] += acc[t][0];
+                s_dw[t * 64 + 2 * lane + 1] += acc[t][1];
+            }
+            s_dw[25 * 64 + 2 * lane] += bsum[0];
+            s_dw[25 * 64 + 2 * lane + 1] += bsum[1];
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for (int i = threadIdx.x; i < 25 * 64; i += kStemWT) atomicAdd(&dw[(i % 64) * 25 + i / 64], s_dw[i]);
     if (threadIdx.x < 64) atomicAdd(&db[threadIdx.x], s_dw[25 * 64 + threadIdx.x]);
 }
@@ -987,13 +994,16 @@ SH_EXPORT int sh_stem_conv_fwd(const void* img, const void* w, const void* b, in
 
 SH_EXPORT int sh_stem_conv_wgrad(const void* img, const void* dy, int N, int S, void* dw, void* db, void* stream) {
     SH_REQUIRE(img && dy && dw && db, "sh_stem_conv_wgrad: null pointer");
+    SH_REQUIRE(S >= 2 && (S & (S - 1)) == 0, "sh_stem_conv_wgrad: S must be a power of two");
     if (N == 0) return SH_OK;
-    const int HW = (S / 2) * (S / 2);
+    const int O = S / 2, HW = O * O;
+    int log2O = 0;
+    while ((1 << log2O) < O) ++log2O;
     int ppb = HW;
-    while (ppb > 384 && (long)N * ((HW + ppb - 1) / ppb) < 6L * SH_NUM_SMS) ppb = (ppb + 1) / 2;
+    while (ppb > 256 && (long)N * ((HW + ppb - 1) / ppb) < 8L * SH_NUM_SMS) ppb = (ppb + 1) / 2;
     dim3 grid(sh_div_up(HW, ppb), N);
-    stem_conv_wgrad_kernel<<<grid, kStemWT, 0, (cudaStream_t)stream>>>((const float*)img, (const __nv_bfloat16*)dy, S, ppb, (float*)dw,
-                                                                       (float*)db);
+    stem_conv_wgrad_kernel<<<grid, kStemWT, 0, (cudaStream_t)stream>>>((const float*)img, (const __nv_bfloat16*)dy, S, log2O, ppb,
+                                                                       (float*)dw, (float*)db);
     SH_CHECK_LAUNCH("stem_conv_wgrad_kernel");
     return SH_OK;
 }

@@ -38,8 +38,9 @@ __device__ __forceinline__ void dense_fwd(const float* __restrict__ wt, const fl
         float acc[RB];
 #pragma unroll
         for (int r = 0; r < RB; ++r) acc[r] = bias[t];
+#pragma unroll 8                 // 8 independent weight loads in flight: the loop is a serial L2-latency chain otherwise
         for (int k = 0; k < n_in; ++k) {
-            const float w = wt[(size_t)k * n_out + t];
+            const float w = __ldg(wt + (size_t)k * n_out + t);
 #pragma unroll
             for (int r = 0; r < RB; ++r) acc[r] += in[r * in_stride + k] * w;
         }
@@ -57,8 +58,9 @@ __device__ __forceinline__ void dense_bwd(const float* __restrict__ w, int n_in,
         float acc[RB];
 #pragma unroll
         for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+#pragma unroll 8
         for (int t = 0; t < n_out; ++t) {
-            const float wv = w[(size_t)t * n_in + k];
+            const float wv = __ldg(w + (size_t)t * n_in + k);
 #pragma unroll
             for (int r = 0; r < RB; ++r) acc[r] += dout[r * dout_stride + t] * wv;
         }

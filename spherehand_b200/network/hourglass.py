@@ -150,6 +150,16 @@ class HourglassNet(nn.Module):
                 wf = self._warena[o_f:o_b].view(taps, cout_pad, cin_pad)
                 wb = self._warena[o_b:o_b + taps * b_rows * b_cols].view(taps, b_rows, b_cols)
                 self._wcache[id(c)] = (wf, wb, cout_pad, cin_pad, b_rows, b_cols)
+            # 3x3 layers: weight gradients accumulate in a [9][Cout][Cin] scratch (vector reductions), unpacked in one launch
+            rows3, off3, self._wg3 = [], 0, {}
+            for c in convs:
+                Cout, Cin, k, _ = c.weight.shape
+                if k == 3:
+                    rows3.append([off3, self._offsets[id(c.weight)][0], Cout, Cin])
+                    self._wg3[id(c)] = (off3, 9 * Cout * Cin)
+                    off3 += 9 * Cout * Cin
+            self._wg3_scratch = torch.zeros(max(off3, 4), device=dev, dtype=torch.float32)
+            self._wg3_table = torch.tensor(rows3 or [[0, 0, 0, 0]], dtype=torch.int32, device=dev)[:len(rows3)].contiguous()
         ops.pack_weights_batch(self._flat, self._wtable, self._warena)
 
     def grad_view(self, p):
@@ -181,7 +191,10 @@ class HourglassNet(nn.Module):
     def run_backward(self, grad_scores):
         """grad_scores: list of fp32 [N,num_outputs,h,w] (or None) -> gradients accumulated into the flat grad buffer."""
         self._flat_grad.zero_()
+        self._wg3_scratch.zero_()
         self._last_run.backward(grad_scores)
+        if self._wg3_table.shape[0]:
+            ops.unpack_wgrad_batch(self._wg3_table, self._wg3_scratch, self._flat_grad)
         return self._flat_grad
 
 
@@ -255,7 +268,11 @@ class _Run:
 
         def bwd(dout, dout_C, need_dx=True, dx_addend=None):
             """dout: bf16 [N,H,W,dout_C] gradient of the conv output -> returns bf16 gradient w.r.t. `a`."""
-            ops.conv_wgrad(dout, a, N, H, W, a_C, Cin, dout_C, Cout, taps, net.grad_view(conv.weight))
+            if taps == 9 and W >= 16 and H >= 4:
+                off3, n3 = net._wg3[id(conv)]
+                ops.conv_wgrad3x3(dout, a, N, H, W, a_C, Cin, dout_C, Cout, net._wg3_scratch[off3:off3 + n3])
+            else:
+                ops.conv_wgrad(dout, a, N, H, W, a_C, Cin, dout_C, Cout, taps, net.grad_view(conv.weight))
             if not need_dx:
                 return None
             dx = torch.empty((N, H, W, a_C), device=self.dev, dtype=BF16)

@@ -216,6 +216,16 @@ def conv_wgrad(dy, x, N, H, W, x_C, Cin, dy_C, Cout, taps, dw):
           _stream())
 
 
+def conv_wgrad3x3(dy, x, N, H, W, x_C, Cin, dy_C, Cout, scratch):
+    _call('sh_conv_wgrad3x3', _chk(dy, BF16, 'dy'), _chk(x, BF16, 'x'), N, H, W, x_C, Cin, dy_C, Cout, _chk(scratch, name='scratch'),
+          _stream())
+
+
+def unpack_wgrad_batch(table, scratch, grad):
+    _call('sh_unpack_wgrad_batch', _chk(table, torch.int32, 'table'), table.shape[0], _chk(scratch, name='scratch'),
+          _chk(grad, name='grad'), _stream())
+
+
 def gn_relu_fwd(x, stats_in, gamma, beta, N, HW, C, G, y, stats_out=None, G_out=16, eps=1e-5):
     _call('sh_gn_relu_fwd', _chk(x, BF16, 'x'), _chk(stats_in, name='stats'), _chk(gamma, name='gamma'), _chk(beta, name='beta'),
           N, HW, C, G, eps, _chk(y, BF16, 'y'), _opt(stats_out, name='stats_out'), G_out, _stream())

@@ -36,7 +36,7 @@ def stats_of(x_nhwc, G):
 
 
 @pytest.mark.parametrize('N,H,Cin,Cout,taps', [(2, 32, 128, 128, 9), (3, 16, 256, 128, 1), (2, 64, 64, 64, 9), (5, 8, 128, 256, 1),
-                                               (4, 4, 128, 128, 9), (2, 32, 256, 82, 1), (2, 32, 64, 128, 1)])
+                                               (4, 4, 128, 128, 9), (2, 32, 256, 82, 1), (2, 32, 64, 128, 1), (3, 16, 128, 128, 9), (1, 64, 64, 64, 9)])
 def test_conv_fwd_dgrad_wgrad(N, H, Cin, Cout, taps):
     torch.manual_seed(N * 100 + H)
     k = 3 if taps == 9 else 1
@@ -82,6 +82,13 @@ def test_conv_fwd_dgrad_wgrad(N, H, Cin, Cout, taps):
     ops.conv_wgrad(dyp, nhwc(x), N, H, H, Cin, Cin, b_cols, Cout, taps, dw)
     ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, padding=k // 2)
     assert rel_err(dw.cpu(), ref_dw.cpu()) < 2e-3
+    if taps == 9 and H >= 16:
+        # kernel-row formulation: [9][Cout][Cin] scratch (accumulating) + batched unpack into the reference layout (+=)
+        scratch = torch.zeros(9 * Cout * Cin, device=DEV)
+        ops.conv_wgrad3x3(dyp, nhwc(x), N, H, H, Cin, Cin, b_cols, Cout, scratch)
+        dw2 = torch.ones_like(w)
+        ops.unpack_wgrad_batch(torch.tensor([[0, 0, Cout, Cin]], dtype=torch.int32, device=DEV), scratch, dw2.view(-1))
+        assert rel_err((dw2 - 1).cpu(), ref_dw.cpu()) < 2e-3
 
 
 @pytest.mark.parametrize('N,H,C,G', [(3, 16, 128, 16), (2, 32, 256, 16), (2, 32, 64, 16), (2, 32, 64, 4)])

@@ -50,9 +50,14 @@ def wgrad_case(H, Cin, Cout, taps):
     k = 3 if taps == 9 else 1
     dw = torch.zeros(Cout, Cin, k, k, device=DEV)
 
+    scratch = torch.zeros(9 * Cout * Cin, device=DEV)
+
     def fn(i):
         j = i % RING
-        ops.conv_wgrad(dys[j], xs[j], N, H, H, Cin, Cin, Cout, Cout, taps, dw)
+        if taps == 9 and H >= 16:
+            ops.conv_wgrad3x3(dys[j], xs[j], N, H, H, Cin, Cin, Cout, Cout, scratch)
+        else:
+            ops.conv_wgrad(dys[j], xs[j], N, H, H, Cin, Cin, Cout, Cout, taps, dw)
     us = timeit(fn)
     flops = 2.0 * N * H * H * Cin * Cout * taps
     byts = N * H * H * 2 * (Cin + Cout)
