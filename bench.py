@@ -138,6 +138,9 @@ def conv_work(name, a):
     if name == 'sh_conv_wgrad':    # (dy,x,N,H,W,x_C,Cin,dy_C,Cout,taps,dw,stream)
         px = float(a[2] * a[3] * a[4])
         return 2.0 * px * a[6] * a[8] * a[9], px * 2 * (a[5] + a[7]), '3x3' if a[9] == 9 else '1x1'
+    if name == 'sh_conv_wgrad3x3':  # (dy,x,N,H,W,x_C,Cin,dy_C,Cout,scratch,stream)
+        px = float(a[2] * a[3] * a[4])
+        return 2.0 * px * a[6] * a[8] * 9, px * 2 * (a[5] + a[7]), '3x3'
     return 0.0, 0.0, ''
 
 
@@ -217,19 +220,22 @@ def run_ours(args, rank, world, local_rank):
                 e2e=dict(value=world * IMAGES_PER_STEP * args.steps / (ms_e2e * 1e-3), unit='images/s', h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=36, ms_per_step=ms_e2e / args.steps))
 
+    # ---- kernel shares + roofline of the dominant kernel family: eager (un-graphed) steps with CUDA events around every
+    #      C-ABI call on the launching stream (the graph replays above cannot be instrumented per kernel).  EVERY rank runs
+    #      these steps (they contain the gradient all-reduce, a collective); only rank 0 records and reports.
+    step.use_graph = False
+    reps = 3
+    for _ in range(2):
+        resident_step()
+    torch.cuda.synchronize()
     if rank == 0:
-        # ---- kernel shares + roofline of the dominant kernel family: one eager (un-graphed) step with CUDA events around
-        #      every C-ABI call on the launching stream (the graph replays above cannot be instrumented per kernel)
-        step.use_graph = False
-        pk = peaks()
-        for _ in range(2):
-            resident_step()
-        torch.cuda.synchronize()
         _lib.PROFILE = []
-        reps = 3
-        for _ in range(reps):
-            resident_step()
-        torch.cuda.synchronize()
+    for _ in range(reps):
+        resident_step()
+    torch.cuda.synchronize()
+    step.use_graph = True
+    if rank == 0:
+        pk = peaks()
         prof, _lib.PROFILE = _lib.PROFILE, None
         fam, cls = {}, {}
         for name, a, e0, e1 in prof:
@@ -239,7 +245,7 @@ def run_ours(args, rank, world, local_rank):
             d['calls'] += 1
             flops, byts, kind = conv_work(name, a)
             if kind:
-                c = cls.setdefault((name, kind), dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
+                c = cls.setdefault(('sh_conv_wgrad' if name == 'sh_conv_wgrad3x3' else name, kind), dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
                 c['ms'] += ms_call; c['calls'] += 1; c['flops'] += flops; c['bytes'] += byts
         total_ms = sum(d['ms'] for d in fam.values())
         shares = {k: round(d['ms'] / total_ms, 4) for k, d in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])[:8]}
@@ -274,7 +280,6 @@ def run_ours(args, rank, world, local_rank):
                 line['roofline']['traffic'] = tr[key]['dram_bytes_per_launch']
                 line['roofline']['traffic_source'] = tr[key]['source']
         line['roofline_other'] = cands[1:] + [r for r in (roof('sh_conv_wgrad', '1x1'), roof('sh_conv_wgrad', '3x3')) if r]
-        step.use_graph = True
         if world == 1:
             base, _ = cpu_arm(1, 1)
             line['cpu_baseline'] = base
