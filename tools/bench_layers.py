@@ -82,6 +82,45 @@ def gn_case(H, C, G=16):
     print('gn_relu_bwd C=%3d @%3d (+add)  : %8.1f us  %7.0f GB/s (vs 4-tensor minimum)' % (C, H, us, byts / us * 1e-3), flush=True)
 
 
+def raster_cases():
+    """The renderers at BASELINE.json's configs: R2 fwd+bwd (config 2: N=256, J=48, 128^2; in-situ N=576, J=41), R1 at the
+    pybind boundary (B=64 meshes of 3382 faces -> 640^2) and on the resize lattice, against the HBM roofline."""
+    import json
+    import numpy as np
+    from spherehand_b200.model import HandModel
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    peak = json.load(open(os.path.join(root, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(root, 'MEASURED_PEAKS.json')) else 6650.0
+    g = torch.Generator(device='cpu').manual_seed(1234)
+    for Nn, J in ((256, 48), (576, 41), (4096, 41)):
+        S = 128
+        c = torch.cat([torch.rand(Nn, J, 2, generator=g) * 180 - 90, torch.rand(Nn, J, 1, generator=g) * 120 - 60], -1).to(DEV)
+        r = (torch.rand(J, generator=g) * 16 + 8).to(DEV)
+        sph = ops.pack_spheres(c, r)
+        depth, idx = ops.sphere_render_fwd(sph, S, S)
+        gd = torch.randn_like(depth) * (idx != 255)
+        fwd_b = Nn * (16 * J + 5 * S * S)
+        bwd_b = Nn * (5 * S * S + 28 * J)
+        us_f = timeit(lambda i: ops.sphere_render_fwd(sph, S, S), reps=30)
+        us_b = timeit(lambda i: ops.sphere_render_bwd(gd, idx, sph), reps=30)
+        print('R2 sphere render N=%4d J=%d 128^2 : fwd %6.1f us %6.0f GB/s (%4.1f%% of measured HBM)   bwd %6.1f us %6.0f GB/s (%4.1f%%)   fwd+bwd %5.1f%%'
+              % (Nn, J, us_f, fwd_b / us_f * 1e-3, 100 * fwd_b / us_f * 1e-3 / peak, us_b, bwd_b / us_b * 1e-3,
+                 100 * bwd_b / us_b * 1e-3 / peak, 100 * (fwd_b + bwd_b) / (us_f + us_b) * 1e-3 / peak), flush=True)
+    hm = dict(np.load(os.path.join(root, 'tests', 'golden', 'hand_model.npz')))
+    hand = HandModel.from_arrays(hm, DEV)
+    B = 64
+    from spherehand_b200 import data
+    poses = data.random_poses(B, g, DEV)
+    mats = ops.fk_fwd(poses, hand.offset_mats, hand.inv_offset_mats)
+    pts = ops.lbs_fwd(mats, *hand.mesh_csr, right_hand=True, mode=2, cam=(320.0, 320.0, 640 / 300, 640 / 300))
+    fv = ops.gather_faces(pts, hand.faces)
+    F = fv.shape[1]
+    us = timeit(lambda i: ops.tri_raster_fwd(fv, 640, 640), reps=10)
+    byts = B * (36 * F + 4 * 640 * 640)
+    print('R1 triangle raster B=%d F=%d -> 640^2 (pybind boundary): %7.1f us %6.0f GB/s (%4.1f%% of measured HBM)' % (B, F, us, byts / us * 1e-3, 100 * byts / us * 1e-3 / peak), flush=True)
+    us = timeit(lambda i: ops.tri_raster_lattice_fwd(fv, 640, 5, 2, 1), reps=10)
+    print('R1 on the 640->128 resize lattice (what the train step runs)  : %7.1f us  (%.1f us per mesh)' % (us, us / B), flush=True)
+
+
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if which in ('all', 'conv'):
@@ -102,6 +141,8 @@ if __name__ == '__main__':
         wgrad_case(16, 128, 128, 9)
         wgrad_case(64, 64, 64, 9)
         wgrad_case(64, 64, 128, 1)
+    if which in ('all', 'raster'):
+        raster_cases()
     if which in ('all', 'gn'):
         gn_case(32, 256)
         gn_case(32, 128)
