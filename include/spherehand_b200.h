@@ -209,6 +209,11 @@ int sh_rand_scale_apply(const void* mats, const void* scales, int B, int nmat, v
 /* torch.clamp(x, max=max_value) of DepthRasterizationFunction.forward (mesh/render.py:286); NaN propagates. */
 int sh_clamp_max(const void* x, long n, float max_value, void* y, void* stream);
 
+/* ResizeCropImage.forward (network/util_modules.py:388-424), all images in one launch: nearest-neighbour resize of image n by
+ * (v_scales[n], u_scales[n]) pasted into the centre of an all-ones canvas.  depth_maps, out [N,H,W]. */
+int sh_resize_crop(const void* depth_maps, const void* u_scales, const void* v_scales, int N, int H, int W, void* out,
+                   void* stream);
+
 /* y = x * s on n fp32 elements: real_dms * depth_scale (network/engine.py:337), xyz / 100 (create_network_and_criterion.py:240). */
 int sh_scale(const void* x, float s, long n, void* y, void* stream);
 

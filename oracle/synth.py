@@ -216,3 +216,32 @@ def depth_noise(dm, nx, ny, nz, sx=0.5, sy=0.5, sz=0.05):
     sv = torch.clamp((ny * sy + 0.5).long() + v, 0, H - 1)
     out = torch.gather(dm.reshape(B, -1), 1, (sv * W + su).reshape(B, -1)).reshape(B, H, W)
     return torch.where(out < 1.0, out + nz * sz, out)
+
+
+def resize_crop(depth_maps, u_scales, v_scales):
+    """ResizeCropImage.forward, network/util_modules.py:388-424, statement by statement (torch CPU): nearest-neighbour
+    resize of every image by (v_scale, u_scale), centred paste into an all-ones canvas.  Reproduces the reference's
+    indentation quirk: the paste sits inside the `else` of `if v_scale > 1`, so an image with v_scale > 1 stays all ones."""
+    import torch.nn.functional as F
+    height, width = depth_maps.shape[-2:]
+    cropped = torch.ones_like(depth_maps)
+    for idx, (dm, u_scale, v_scale) in enumerate(zip(depth_maps, u_scales, v_scales)):
+        dm = dm.view(1, 1, height, width)
+        new_size = (int(height * v_scale + 0.5), int(width * u_scale + 0.5))
+        resized = F.interpolate(dm, new_size)
+        if u_scale > 1:
+            u_start, u_end = 0, width
+            orig_u_start = (int(width * u_scale + 0.5) - width) // 2
+            orig_u_end = orig_u_start + width
+        else:
+            orig_u_start, orig_u_end = 0, int(width * u_scale)
+            u_start = (width - int(width * u_scale + 0.5)) // 2
+            u_end = u_start + orig_u_end
+        if v_scale > 1:
+            pass
+        else:
+            orig_v_start, orig_v_end = 0, int(height * v_scale)
+            v_start = (height - int(height * v_scale + 0.5)) // 2
+            v_end = v_start + orig_v_end
+            cropped[idx, v_start:v_end, u_start:u_end] = resized[0, 0, orig_v_start:orig_v_end, orig_u_start:orig_u_end]
+    return cropped.squeeze()

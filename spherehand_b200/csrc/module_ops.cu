@@ -117,6 +117,36 @@ __global__ void rand_scale_kernel(const float* __restrict__ mats, const float* _
     out[i] = row < 3 ? scales[b * 3 + row] * mats[i] : mats[i];
 }
 
+// ResizeCropImage.forward (network/util_modules.py:388-424): nearest-neighbour resize by (v_scale, u_scale) pasted into the
+// centre of an all-ones canvas, all images in one launch (the reference loops over images in Python, one interpolate
+// each).  The integer geometry is evaluated with the reference's fp32 expressions: int(size*scale + 0.5), int(size*scale),
+// floor(dst * (in/out)) of F.interpolate(mode='nearest').  An image with v_scale > 1 stays all ones (the reference's paste
+// sits inside the `else` of `if v_scale > 1`).
+__global__ void resize_crop_kernel(const float* __restrict__ in, const float* __restrict__ us, const float* __restrict__ vs, int H, int W,
+                                   float* __restrict__ out) {
+    const int n = blockIdx.y;
+    const float u = us[n], v = vs[n];
+    const int new_w = (int)__fadd_rn(__fmul_rn((float)W, u), 0.5f), new_h = (int)__fadd_rn(__fmul_rn((float)H, v), 0.5f);
+    int u_start, u_cnt, ou_start;
+    if (u > 1.f) { u_start = 0; u_cnt = W; ou_start = (new_w - W) / 2; }
+    else { ou_start = 0; u_cnt = (int)__fmul_rn((float)W, u); u_start = (W - new_w) / 2; }
+    const bool paste = !(v > 1.f);
+    const int v_cnt = (int)__fmul_rn((float)H, v), v_start = (H - new_h) / 2;
+    const float sx = new_w > 0 ? (float)W / (float)new_w : 0.f, sy = new_h > 0 ? (float)H / (float)new_h : 0.f;
+    const float* img = in + (size_t)n * H * W;
+    float* dst = out + (size_t)n * H * W;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < H * W; p += gridDim.x * blockDim.x) {
+        const int y = p / W, x = p - y * W;
+        float val = 1.f;
+        if (paste && y >= v_start && y < v_start + v_cnt && x >= u_start && x < u_start + u_cnt) {
+            const int ry = y - v_start, rx = ou_start + (x - u_start);                 // position in the resized image
+            const int iy = min((int)floorf(__fmul_rn((float)ry, sy)), H - 1), ix = min((int)floorf(__fmul_rn((float)rx, sx)), W - 1);
+            val = img[iy * W + ix];
+        }
+        dst[p] = val;
+    }
+}
+
 __global__ void clamp_max_kernel(const float* __restrict__ x, long n, float mx, float* __restrict__ y) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const float v = x[i]; y[i] = (v != v) ? v : fminf(v, mx); }   // NaN propagates like torch.clamp
@@ -181,5 +211,18 @@ SH_EXPORT int sh_clamp_max(const void* x, long n, float max_value, void* y, void
     if (n <= 0) return SH_OK;
     clamp_max_kernel<<<sh_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, n, max_value, (float*)y);
     SH_CHECK_LAUNCH("clamp_max_kernel");
+    return SH_OK;
+}
+
+// depth_maps [N,H,W], u_scales / v_scales [N] -> out [N,H,W]
+SH_EXPORT int sh_resize_crop(const void* depth_maps, const void* u_scales, const void* v_scales, int N, int H, int W, void* out,
+                              void* stream) {
+    SH_REQUIRE(N >= 0 && H >= 1 && W >= 1 && N <= 65535, "sh_resize_crop: bad N/H/W");
+    if (N == 0) return SH_OK;
+    SH_REQUIRE(depth_maps && u_scales && v_scales && out, "sh_resize_crop: null pointer");
+    dim3 grid(sh_div_up((long)H * W, 1024) < 16 ? sh_div_up((long)H * W, 1024) : 16, N);
+    resize_crop_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)depth_maps, (const float*)u_scales, (const float*)v_scales,
+                                                                H, W, (float*)out);
+    SH_CHECK_LAUNCH("resize_crop_kernel");
     return SH_OK;
 }

@@ -1,7 +1,8 @@
 """Drop-in mirror of the hot-path parts of /root/reference/network/util_modules.py: DepthNoise (:46-84),
 HandSynthesizer (:86-122), RecoverXYZCoordinateFromHeatmap (:164-201).  Off-path classes of that file (DepthResample,
 HeatmapVariance, PosePriorLoss, DepthSegmentation, TemporalSmoothnessLoss; flag-gated or unused) are not
-mirrored.  `ResizeCropImage` (:383-424, the per-image scale augmentation) is a "next" row of SURVEY.md §8f.
+mirrored.  `ResizeCropImage` (:383-424, the per-image scale augmentation; a "next" row of SURVEY.md §8f-2) runs as one
+batched kernel instead of a Python loop with one interpolate per image.
 """
 import numpy as np
 import torch
@@ -113,3 +114,17 @@ class RecoverXYZCoordinateFromHeatmap(nn.Module):
         """u,v = sum softmax(20 hm) * grid; d = sum d_hm * relu(hm)/(sum relu(hm) + 1e-5); -> xyz [N,J,3] in mm (:182-201)."""
         assert uv_hms.shape[-1] == self.u_grid.shape[-1] and uv_hms.shape[-2] == self.u_grid.shape[-2], 'heat-map size mismatch'
         return _SoftArgmaxFunction.apply(uv_hms, d_hms, self.depth_scale)
+
+
+class ResizeCropImage(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.sigma_z = 0.05
+
+    def forward(self, depth_maps, u_scales, v_scales):
+        """depth_maps [N,H,W], u_scales / v_scales [N] -> [N,H,W].squeeze(): every image resized (nearest) by its own scale
+        and pasted into the centre of an all-ones canvas (:388-424).  No gradient (it augments the network INPUT)."""
+        n = depth_maps.shape[0]
+        dm = depth_maps.detach().reshape(n, depth_maps.shape[-2], depth_maps.shape[-1]).contiguous().float()
+        out = ops.resize_crop(dm, u_scales.detach().reshape(-1).contiguous().float(), v_scales.detach().reshape(-1).contiguous().float())
+        return out.squeeze()

@@ -359,6 +359,14 @@ def clamp_max(x, max_value):
     return out
 
 
+def resize_crop(depth_maps, u_scales, v_scales):
+    N, H, W = depth_maps.shape
+    out = torch.empty_like(depth_maps)
+    _call('sh_resize_crop', _chk(depth_maps, name='depth_maps'), _chk(u_scales, name='u_scales'), _chk(v_scales, name='v_scales'),
+          N, H, W, out.data_ptr(), _stream())
+    return out
+
+
 def scale(x, s, out):
     _call('sh_scale', _chk(x, name='x'), float(s), x.numel(), _chk(out, name='out'), _stream())
     return out

@@ -174,6 +174,26 @@ def test_synth_modules_against_golden_and_oracle(hand_model):
         htm(cu(fk['params']).requires_grad_(True))                                # forward-only, loudly
 
 
+def test_resize_crop_image_against_golden_and_oracle():
+    """ResizeCropImage (util_modules.py:383-424) as one batched kernel: bit-exact against the reference fixture and, on
+    random scales in the range MultiTaskLoss draws (create_network_and_criterion.py:99-101) and beyond, against the oracle."""
+    g = golden('resize_crop')
+    rc = util_modules.ResizeCropImage().to(DEV)
+    for S in (64, 128):
+        out = rc(cu(g['dm%d' % S]), cu(g['u%d' % S]), cu(g['v%d' % S]))
+        assert np.array_equal(out.cpu().numpy(), g['out%d' % S])
+    gen = torch.Generator().manual_seed(5)
+    for (n, H, W) in ((192, 128, 128), (7, 48, 80), (1, 64, 64)):
+        dm = torch.rand(n, H, W, generator=gen)
+        u = torch.rand(n, generator=gen) * 0.7 + 0.5
+        v = torch.rand(n, generator=gen) * 0.7 + 0.5
+        out = rc(dm.to(DEV), u.to(DEV), v.to(DEV))
+        assert torch.equal(out.cpu(), synth.resize_crop(dm, u, v))
+    assert rc(torch.zeros(0, 8, 8, device=DEV), torch.zeros(0, device=DEV), torch.zeros(0, device=DEV)).numel() == 0
+    with pytest.raises(spherehand_b200.SphereHandError):
+        rc(torch.rand(2, 8, 8), torch.ones(2), torch.ones(2))                      # host tensors: no CPU fallback
+
+
 def test_network_heads_and_full_criterion(hand_model):
     # soft-argmax head through autograd
     g = golden('softargmax')
