@@ -38,7 +38,7 @@ __device__ __forceinline__ void dense_fwd(const float* __restrict__ wt, const fl
         float acc[RB];
 #pragma unroll
         for (int r = 0; r < RB; ++r) acc[r] = bias[t];
-#pragma unroll 8                 // 8 independent weight loads in flight: the loop is a serial L2-latency chain otherwise
+#pragma unroll 32                // 32 independent weight loads in flight: the loop is a serial L2-latency chain otherwise
         for (int k = 0; k < n_in; ++k) {
             const float w = __ldg(wt + (size_t)k * n_out + t);
 #pragma unroll
@@ -58,7 +58,7 @@ __device__ __forceinline__ void dense_bwd(const float* __restrict__ w, int n_in,
         float acc[RB];
 #pragma unroll
         for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-#pragma unroll 8
+#pragma unroll 32
         for (int t = 0; t < n_out; ++t) {
             const float wv = __ldg(w + (size_t)t * n_in + k);
 #pragma unroll

@@ -1,3 +1,5 @@
+// Result on B200 (gpurun, round 1): K-major SWIZZLE_128B descriptors with base_offset 0 address correctly for EVERY row shift and
+// for 8-row group pitches of 8, 10, 16 and 18 rows (SBO 1024 / 1280 / 2048 / 2304 B); base_offset != 0 is wrong for shifted starts.
 // Probe: does a tcgen05 shared-memory descriptor whose start address is shifted by whole 128-byte rows (not 1024-byte aligned)
 // address the rows TMA wrote with SWIZZLE_128B?  Decides whether a 3x3 convolution can derive its nine taps from ONE halo
 // tile in shared memory (start shifted by dw rows, 8-row groups `sbo` bytes apart) instead of nine TMA boxes.
@@ -112,7 +114,8 @@ int main() {
     for (int bo = 0; bo < 2; ++bo) {
         for (int sh : {0, 1, 2, 3, 7, 8, 9, 17}) cases.push_back({0, sh, 8, bo});      // contiguous groups, shifted start
         for (int sh : {0, 1, 2, 17, 18, 34}) cases.push_back({0, sh, 16, bo});         // halo pitch 16 rows (SBO 2048)
-        for (int sh : {0, 1, 2, 19}) cases.push_back({0, sh, 18, bo});                 // halo pitch 18 rows (SBO 2304, not 1024-aligned)
+        for (int sh : {0, 1, 2, 13}) cases.push_back({0, sh, 18, bo});                 // halo pitch 18 rows (SBO 2304, not 1024-aligned)
+        for (int sh : {0, 1, 2, 10, 11, 12, 20, 21, 22}) cases.push_back({0, sh, 10, bo});   // halo pitch 10 rows (SBO 1280): the 8x16 tile of a 3x3 conv
         for (int sh : {0, 1, 2, 3, 9, 19}) cases.push_back({1, sh, 8, bo});            // MN-major, shifted K rows
     }
     for (const Case& c : cases) {
