@@ -39,6 +39,14 @@ constexpr int kABytes = kBM * kBK * 2;          // 16 KB
 constexpr int kStgBytes = kBM * 64 * 2;         // 16 KB: 128 pixels x 64 channels bf16
 constexpr int kSmemLimit = 232448;              // 227 KB opt-in maximum per CTA
 constexpr int kIdentBytes = 64 * 128;           // K-major 64x64 identity tile
+// ---- halo mode (3x3, images >= 16x8): ONE TMA box {64 ch, 10, 18} per (tile, k-block) instead of nine 16 KB tap boxes; the
+// nine taps are UMMA descriptors into that halo tile (start shifted by (dh+1)*10 + (dw+1) rows of 128 B, 8-row groups one
+// halo row = 1280 B apart: tools/umma_probe.cu), and every weight tile is used for TWO pixel tiles (four TMEM accumulators),
+// so L2 -> SM traffic per 128 pixels drops from 576 KB to 190 KB at Cin = Cout = 128.
+constexpr int kHaloW = 10, kHaloH = 18;         // tile 8 x 16 pixels + 1-pixel border
+constexpr int kHaloBytes = kHaloW * kHaloH * 128;            // 23,040 B
+constexpr int kHaloSlotBytes = (kHaloBytes + 1023) / 1024 * 1024;
+constexpr int kHaloSlots = 4;                   // two tiles of the current k-block + two of the next
 
 struct ConvGeom {
     int N, H, W;
@@ -143,7 +151,7 @@ __device__ __forceinline__ void row_stats(const uint32_t (&packed)[NW], bool row
     }
 }
 
-template <int BN>
+template <int BN, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmRes,
@@ -152,9 +160,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kBBytes = BN * kBK * 2;                       // one (tap, k-block) weight tile
+    constexpr int NACC = HALO ? 4 : 2;                          // TMEM accumulator buffers
     const int num_k = g.taps * g.kblocks;
-    const int stage_bytes = kABytes + (g.b_resident ? 0 : kBBytes);
-    uint8_t* s_pipe = smem;
+    // halo mode: the ring holds weight tiles only (the activation halos have their own slots in front of it)
+    const int stage_bytes = HALO ? kBBytes : kABytes + (g.b_resident ? 0 : kBBytes);
+    uint8_t* s_halo = smem;
+    uint8_t* s_pipe = smem + (HALO ? kHaloSlots * kHaloSlotBytes : 0);
     uint8_t* s_bres = s_pipe + g.stages * stage_bytes;          // resident weights (size 0 when streamed)
     uint8_t* s_ident = s_bres + (g.b_resident ? num_k * kBBytes : 0);   // 64x64 bf16 identity (residual add on the tensor core)
     uint8_t* s_stg = s_ident + (g.has_res ? kIdentBytes : 0);
@@ -162,10 +173,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
     uint64_t* full_bar = bars;                                  // [kMaxStages]
     uint64_t* empty_bar = bars + kMaxStages;                    // [kMaxStages]
     uint64_t* b_full = bars + 2 * kMaxStages;                   // [1]
-    uint64_t* acc_full = b_full + 1;                            // [2]
-    uint64_t* acc_empty = acc_full + 2;                         // [2]
-    uint64_t* res_full = acc_empty + 2;                         // [kGroups]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + kGroups);
+    uint64_t* acc_full = b_full + 1;                            // [4]
+    uint64_t* acc_empty = acc_full + 4;                         // [4]
+    uint64_t* halo_full = acc_empty + 4;                        // [kHaloSlots]
+    uint64_t* halo_empty = halo_full + kHaloSlots;              // [kHaloSlots]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(halo_empty + kHaloSlots);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);    // [256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,8 +190,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
         for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(b_full, 1);
         // a buffer is drained by one group (single-chunk layers) or by the two groups that split its chunks
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], g.nchunks >= 2 ? 256 : 128); }
-        for (int s = 0; s < kGroups; ++s) mbar_init(&res_full[s], 1);
+        for (int b = 0; b < 4; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], g.nchunks >= 2 ? 256 : 128); }
+        for (int s = 0; s < kHaloSlots; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], 1); }
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < 256; i += kThreads) s_bias[i] = (p.bias && i < g.cout) ? p.bias[i] : 0.f;
@@ -193,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
         }
         fence_async_smem();                                     // generic-proxy writes -> visible to tcgen05.mma
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    if (warp == 1) tmem_alloc(tmem_slot, NACC * BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -201,6 +213,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
 
     if (warp == 0) {
         // ===================== TMA producer (one elected lane) =====================
+        if constexpr (HALO) {
+            if (lane == 0) {
+                // item sequence of this CTA: super-tiles of two pixel tiles; per k-block two halos and nine weight tiles.
+                const int my_tiles = (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+                const int n_items = ((my_tiles + 1) / 2) * g.kblocks;
+                int hit = 0;                                        // halo slots issued so far
+                auto issue_halos = [&](int item) {
+                    const int st = item / g.kblocks, kb = item - st * g.kblocks;
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const int tl = 2 * st + sub;
+                        if (tl >= my_tiles) break;
+                        const TileCoord t = tile_coord(g, blockIdx.x + tl * gridDim.x);
+                        const int hs = hit % kHaloSlots, hph = (hit / kHaloSlots) & 1;
+                        ++hit;
+                        mbar_wait(&halo_empty[hs], hph ^ 1);
+                        mbar_expect_tx(&halo_full[hs], (uint32_t)kHaloBytes);
+                        tma_load_4d(s_halo + hs * kHaloSlotBytes, &tmA, &halo_full[hs], kb * kBK, t.w0 - 1, t.h0 - 1, t.n0);
+                    }
+                };
+                if (n_items > 0) issue_halos(0);
+                int it = 0;
+                for (int item = 0; item < n_items; ++item) {
+                    const int kb = item % g.kblocks;
+                    for (int tap = 0; tap < 9; ++tap, ++it) {
+                        // the next item's halos go out after four weight tiles of this one: by then (ring of >= 4 slots) the
+                        // MMA has started this item, i.e. the slots of item-1 are free and the wait below cannot hold up the
+                        // weight stream; they then have five taps (~2500 MMA cycles) to land
+                        if (tap == 4 && item + 1 < n_items) issue_halos(item + 1);
+                        const int s = it % g.stages, ph = (it / g.stages) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_expect_tx(&full_bar[s], (uint32_t)kBBytes);
+                        tma_load_2d(s_pipe + s * stage_bytes, &tmB, &full_bar[s], kb * kBK, tap * g.cout_pad);
+                    }
+                }
+            }
+        } else
         if (lane == 0) {
             if (g.b_resident) {
                 mbar_expect_tx(b_full, (uint32_t)(num_k * kBBytes));
@@ -235,6 +283,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one elected lane) =====================
+        if constexpr (HALO) {
+            if (lane == 0) {
+                constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+                const int my_tiles = (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+                int it = 0, hit = 0;
+                for (int tl0 = 0; tl0 < my_tiles; tl0 += 2) {
+                    const int nsub = tl0 + 1 < my_tiles ? 2 : 1;
+                    for (int sub = 0; sub < nsub; ++sub)            // the epilogue has drained these accumulators
+                        mbar_wait(&acc_empty[(tl0 + sub) & 3], (uint32_t)((((tl0 + sub) >> 2) & 1) ^ 1));
+                    tc_fence_after();
+                    for (int kb = 0; kb < g.kblocks; ++kb) {
+                        uint32_t halo_addr[2];
+                        int hslot[2];
+                        for (int sub = 0; sub < nsub; ++sub, ++hit) {
+                            hslot[sub] = hit % kHaloSlots;
+                            mbar_wait(&halo_full[hslot[sub]], (uint32_t)((hit / kHaloSlots) & 1));
+                            halo_addr[sub] = smem_u32(s_halo + hslot[sub] * kHaloSlotBytes);
+                        }
+                        tc_fence_after();
+                        for (int tap = 0; tap < 9; ++tap, ++it) {
+                            const int s = it % g.stages, ph = (it / g.stages) & 1;
+                            mbar_wait(&full_bar[s], ph);
+                            tc_fence_after();
+                            const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(s_pipe + s * stage_bytes));
+                            const uint32_t shift = (uint32_t)((tap / 3) * kHaloW + tap % 3) * 128u;     // (dh+1)*10 + (dw+1) rows
+                            for (int sub = 0; sub < nsub; ++sub) {
+                                const uint64_t ad = umma_desc_kmajor_sw128_sbo(halo_addr[sub] + shift, kHaloW * 128);
+                                const uint32_t d_tmem = tmem_base + (uint32_t)(((tl0 + sub) & 3) * BN);
+#pragma unroll
+                                for (int kk = 0; kk < kBK / 16; ++kk)
+                                    umma_bf16(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (kb | tap | kk) != 0);
+                            }
+                            umma_commit(&empty_bar[s]);             // frees the weight slot when these MMAs retire
+                        }
+                        for (int sub = 0; sub < nsub; ++sub) umma_commit(&halo_empty[hslot[sub]]);
+                    }
+                    for (int sub = 0; sub < nsub; ++sub) umma_commit(&acc_full[(tl0 + sub) & 3]);
+                }
+            }
+        } else
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
             if (g.b_resident) mbar_wait(b_full, 0);
@@ -297,7 +385,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
             const TileCoord t = tile_coord(g, tile);
             const int n = t.n0 + ln, h = t.h0 + lh, w = t.w0 + lw;
             const bool row_ok = n < g.N;
-            mbar_wait(&acc_full[buf], lt & 1);
+            const int tl = buf + 2 * lt;                        // local tile index; its accumulator and barrier phase
+            const int abuf = tl & (NACC - 1);
+            mbar_wait(&acc_full[abuf], (uint32_t)((tl / NACC) & 1));
             tc_fence_after();
             for (int c = half; c < g.nchunks; c += 2) {
                 const int cg = c * 64;                          // first channel of this chunk
@@ -308,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
 #pragma unroll 1
                 for (int hh = 0; hh < 2; ++hh) {                // 32 accumulator columns at a time
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + cg + hh * 32), v);
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(abuf * BN + cg + hh * 32), v);
                     tmem_ld_wait();
                     const int ch0 = cg + hh * 32;
                     uint32_t packed[16];
@@ -360,13 +450,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
                 }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);                       // 128 arrivals per serving group free the accumulator buffer
+            mbar_arrive(&acc_empty[abuf]);                      // 128 arrivals per serving group free the accumulator buffer
         }
         if (issuer) bulk_wait_all();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+    if (warp == 1) tmem_dealloc(tmem_base, NACC * BN);
 }
 
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
@@ -378,15 +468,15 @@ int make_act_tmap(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
     return sh_make_tmap_bf16(m, base, 4, dims, strides, box);
 }
 
-template <int BN>
+template <int BN, bool HALO>
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmRes, const CUtensorMap& tmOut,
                 const ConvGeom& g, const ConvPtrs& p, int grid, size_t smem, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        SH_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        SH_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr = true;
     }
-    conv_fwd_kernel<BN><<<grid, kThreads, smem, st>>>(tmA, tmB, tmRes, tmOut, g, p);
+    conv_fwd_kernel<BN, HALO><<<grid, kThreads, smem, st>>>(tmA, tmB, tmRes, tmOut, g, p);
     SH_CHECK_LAUNCH("conv_fwd_kernel");
     return SH_OK;
 }
@@ -414,7 +504,11 @@ SH_EXPORT int sh_conv_fwd(const void* x, const void* w, const void* bias, const 
     cudaStream_t st = (cudaStream_t)stream;
     ConvGeom g;
     g.N = N; g.H = H; g.W = W;
-    g.bw = W < 16 ? W : 16;
+    // halo mode: 3x3 without a residual on images that hold an 8 x 16 pixel tile; SH_CONV_HALO=0 keeps the nine-box path
+    const char* halo_env = getenv("SH_CONV_HALO");          // read per call: the parity tests flip it inside one process
+    const bool halo_on = !halo_env || atoi(halo_env) != 0;
+    const bool halo = halo_on && taps == 9 && !residual && H >= 16 && W >= 8 && cout_pad <= 128;
+    g.bw = halo ? 8 : (W < 16 ? W : 16);
     g.bh = H < 128 / g.bw ? H : 128 / g.bw;
     g.bn = 128 / (g.bw * g.bh);
     SH_REQUIRE(g.bn <= 8, "sh_conv_fwd: image too small");
@@ -432,34 +526,47 @@ SH_EXPORT int sh_conv_fwd(const void* x, const void* w, const void* bias, const 
     const long resident = (long)num_k * b_tile;
     size_t smem = 0;
     {
-        const int fixed = 1024 /*alignment*/ + kGroups * kStgBytes + 2048 /*barriers + bias*/ + (residual ? kIdentBytes : 0);
+        const int fixed = 1024 /*alignment*/ + kGroups * kStgBytes + 2048 /*barriers + bias*/ + (residual ? kIdentBytes : 0) +
+                          (halo ? kHaloSlots * kHaloSlotBytes : 0);
         const int avail = kSmemLimit - fixed;
-        if (resident + 2 * kABytes <= avail) {
+        if (halo) {
+            g.b_resident = 0;
+            g.stages = avail / b_tile;
+            if (g.stages > kMaxStages) g.stages = kMaxStages;
+            smem = (size_t)fixed + (size_t)g.stages * b_tile;
+        } else if (resident + 2 * kABytes <= avail) {
             g.b_resident = 1;
             g.stages = (int)((avail - resident) / kABytes);
         } else {
             g.b_resident = 0;
             g.stages = avail / (kABytes + b_tile);
         }
-        if (g.stages > kMaxStages) g.stages = kMaxStages;
-        smem = (size_t)fixed + (size_t)g.stages * (kABytes + (g.b_resident ? 0 : b_tile)) + (g.b_resident ? resident : 0);
+        if (!halo) {
+            if (g.stages > kMaxStages) g.stages = kMaxStages;
+            smem = (size_t)fixed + (size_t)g.stages * (kABytes + (g.b_resident ? 0 : b_tile)) + (g.b_resident ? resident : 0);
+        }
     }
     SH_REQUIRE(g.stages >= 2, "sh_conv_fwd: shared-memory plan failed");
     ConvPtrs p{(const float*)bias, (float*)y_nchw, (float*)stats};
     CUtensorMap tmA, tmB, tmRes, tmOut;
-    int rc = make_act_tmap(&tmA, x, N, H, W, Cin, g.bw, g.bh, g.bn);
+    int rc = halo ? make_act_tmap(&tmA, x, N, H, W, Cin, kHaloW, kHaloH, 1) : make_act_tmap(&tmA, x, N, H, W, Cin, g.bw, g.bh, g.bn);
     if (rc) return rc;
     const uint64_t wd[2] = {(uint64_t)Cin, (uint64_t)taps * cout_pad};
     const uint64_t ws[1] = {(uint64_t)Cin * 2};
     const uint32_t wb[2] = {64, (uint32_t)cout_pad};
     rc = sh_make_tmap_bf16(&tmB, w, 2, wd, ws, wb);
     if (rc) return rc;
-    tmRes = tmA;
-    tmOut = tmA;
+    rc = make_act_tmap(&tmRes, x, N, H, W, Cin, g.bw, g.bh, g.bn);      // placeholders unless replaced below
+    if (rc) return rc;
+    tmOut = tmRes;
     if (residual) { rc = make_act_tmap(&tmRes, residual, N, H, W, Cout, g.bw, g.bh, g.bn); if (rc) return rc; }
     if (y) { rc = make_act_tmap(&tmOut, y, N, H, W, y_ld, g.bw, g.bh, g.bn); if (rc) return rc; }
     const int grid = g.num_tiles < SH_NUM_SMS ? g.num_tiles : SH_NUM_SMS;
-    if (cout_pad == 256) return launch_conv<256>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
-    if (cout_pad == 128) return launch_conv<128>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
-    return launch_conv<64>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+    if (halo) {
+        if (cout_pad == 128) return launch_conv<128, true>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+        return launch_conv<64, true>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+    }
+    if (cout_pad == 256) return launch_conv<256, false>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+    if (cout_pad == 128) return launch_conv<128, false>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+    return launch_conv<64, false>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
 }

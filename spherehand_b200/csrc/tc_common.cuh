@@ -102,6 +102,18 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                               // layout: SWIZZLE_128B
     return d;
 }
+// Same, with the 8-row groups `sbo_bytes` apart (a multiple of 128) and a start address on ANY 128-byte row: the swizzle is a
+// function of the shared-memory address bits, so a window into a larger TMA-written tile addresses correctly with
+// base_offset 0 (measured: tools/umma_probe.cu).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // MN-major operand tile, 128-byte swizzle: each K index is one 128-byte row of 64 contiguous MN elements;
 // 8 K-rows form a 1024 B group (SBO); successive 64-element MN chunks are `lbo_bytes` apart (LBO).
 __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {

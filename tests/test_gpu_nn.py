@@ -4,6 +4,8 @@ Floating-point kernels: the comparison is against plain PyTorch fp32 (TF32 disab
 for single layers on operands already rounded to bf16 (so only accumulation order and the bf16 output rounding
 differ: tolerance 1e-2 of the tensor's max), for the whole network against the fp32 oracle / the golden fixtures
 of the reference (tolerance 2e-2 on heat-maps, 5e-2 on gradients: bf16 operand contract)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -89,6 +91,41 @@ def test_conv_fwd_dgrad_wgrad(N, H, Cin, Cout, taps):
         dw2 = torch.ones_like(w)
         ops.unpack_wgrad_batch(torch.tensor([[0, 0, Cout, Cin]], dtype=torch.int32, device=DEV), scratch, dw2.view(-1))
         assert rel_err((dw2 - 1).cpu(), ref_dw.cpu()) < 2e-3
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(40, 32, 32, 128, 128), (19, 16, 16, 128, 128), (5, 64, 64, 64, 64), (75, 16, 8, 256, 128),
+                                            (2, 32, 32, 128, 82)])
+def test_conv3x3_halo_mode(N, H, W, Cin, Cout):
+    """3x3 without a residual on images >= 16x8 takes the halo path (one TMA halo box per k-block, nine shifted UMMA
+    descriptors, two pixel tiles per weight tile): CTAs with 1, 2 and 3 tiles, odd tile counts, image borders, 2 and 4 k-blocks."""
+    torch.manual_seed(N + H + Cin)
+    x = torch.randn(N, Cin, H, W, device=DEV).to(BF16).float()
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, device=DEV)
+    ref = F.conv2d(x, w.to(BF16).float(), b, padding=1)
+    cout_pad = (Cout + 127) // 128 * 128 if Cout > 64 else 64
+    y_ld = cout_pad if Cout % 8 else Cout
+    wf = torch.empty((9, cout_pad, Cin), device=DEV, dtype=BF16)
+    ops.pack_weights(w, Cout, Cin, 9, cout_pad, Cin, wf)
+    y = torch.zeros((N, H, W, y_ld), device=DEV, dtype=BF16)
+    y32 = torch.empty((N, Cout, H, W), device=DEV)
+    G = 16 if Cout % 16 == 0 else 0
+    st = torch.zeros((N, 16, 2), device=DEV)
+    ops.conv_fwd(nhwc(x), wf, b, N, H, W, Cin, Cout, cout_pad, 9, y=y, y_ld=y_ld, y_nchw=y32, stats=st if G else None, groups=16)
+    torch.cuda.synchronize()
+    assert rel_err(y32.cpu(), ref.cpu()) < 2e-3
+    assert rel_err(nchw(y)[:, :Cout].cpu(), ref.cpu()) < 1e-2
+    if G:
+        assert rel_err(st.cpu(), stats_of(y, 16).cpu()) < 1e-3
+    # the nine-box path (SH_CONV_HALO=0, read per call) on the same input: fp32 results equal up to accumulation order
+    os.environ['SH_CONV_HALO'] = '0'
+    try:
+        y32b = torch.empty_like(y32)
+        ops.conv_fwd(nhwc(x), wf, b, N, H, W, Cin, Cout, cout_pad, 9, y=torch.empty_like(y), y_ld=y_ld, y_nchw=y32b)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ['SH_CONV_HALO']
+    assert rel_err(y32.cpu(), y32b.cpu()) < 1e-5
 
 
 @pytest.mark.parametrize('N,H,C,G', [(3, 16, 128, 16), (2, 32, 256, 16), (2, 32, 64, 16), (2, 32, 64, 4)])
