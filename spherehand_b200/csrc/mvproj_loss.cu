@@ -50,6 +50,12 @@ __global__ void mvproj_prep_kernel(const float* __restrict__ cam, const float* _
     }
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int PX>
 __global__ void __launch_bounds__(kThreads) mvproj_main_kernel(
     const float4* __restrict__ spheres, const float* __restrict__ real, int V, int J, int H, int W,
@@ -57,11 +63,11 @@ __global__ void __launch_bounds__(kThreads) mvproj_main_kernel(
     float4* __restrict__ gsph, double* __restrict__ acc) {
     __shared__ __align__(128) float4 s_sph[kMaxJ];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ float s_acc[kMaxJ * 3];
+    __shared__ __align__(16) float s_acc[kThreads / 32][kMaxJ * 4];      // one private gradient table per warp (dcx, dcy, dcz, -)
     __shared__ float s_loss[2];
     const int pair = blockIdx.y;
     const int j = pair % V, i = (pair / V) % V, b = pair / (V * V);
-    for (int t = threadIdx.x; t < kMaxJ * 3; t += kThreads) s_acc[t] = 0.f;
+    for (int t = threadIdx.x; t < (kThreads / 32) * kMaxJ * 4; t += kThreads) (&s_acc[0][0])[t] = 0.f;
     if (threadIdx.x < 2) s_loss[threadIdx.x] = 0.f;
     stage_spheres(s_sph, &s_bar, spheres + (size_t)pair * J, J);
 
@@ -75,6 +81,7 @@ __global__ void __launch_bounds__(kThreads) mvproj_main_kernel(
     const float* real_img = real + ((size_t)b * V + j) * H * W;
     float* proj_img = projected + (size_t)pair * H * W;
     float l_m2d = 0.f, l_d2m = 0.f;
+    float* acc_w = s_acc[threadIdx.x >> 5];
 
     for (int t = t_begin + warp; t < t_end; t += kThreads / 32) {
         const int ty = t / g.tiles_x, tx = t - ty * g.tiles_x;
@@ -134,54 +141,70 @@ __global__ void __launch_bounds__(kThreads) mvproj_main_kernel(
                 }
             }
         }
-        if (!active) continue;
         const size_t o = (size_t)r * W + c;
         float z[PX];
-        if (PX == 4) {
-            *reinterpret_cast<float4*>(proj_img + o) = make_float4(best[0], best[1 % PX], best[2 % PX], best[3 % PX]);
-            const float4 zv = *reinterpret_cast<const float4*>(real_img + o);
-            z[0] = zv.x; z[1 % PX] = zv.y; z[2 % PX] = zv.z; z[3 % PX] = zv.w;
-        } else {
-            proj_img[o] = best[0];
-            z[0] = real_img[o];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) z[p] = SH_BACKGROUND;
+        if (active) {
+            if (PX == 4) {
+                *reinterpret_cast<float4*>(proj_img + o) = make_float4(best[0], best[1 % PX], best[2 % PX], best[3 % PX]);
+                const float4 zv = *reinterpret_cast<const float4*>(real_img + o);
+                z[0] = zv.x; z[1 % PX] = zv.y; z[2 % PX] = zv.z; z[3 % PX] = zv.w;
+            } else {
+                proj_img[o] = best[0];
+                z[0] = real_img[o];
+            }
         }
-        if (wpx == 0.f) continue;
+        if (wpx == 0.f) continue;                          // block-uniform: off-diagonal pair of a single-view step
+        // Gradients go to the warp's private table through warp_accumulate (shuffle sums per distinct sphere, one plain
+        // read-modify-write): the shared-memory float atomics this replaces are CAS loops, 32-way contended inside a sphere.
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
             // ---- model -> data: (proj - real)^2, gradient through the arg-min sphere
-            const float diff = best[p] - z[p];
+            const float diff = active ? best[p] - z[p] : 0.f;
             l_m2d += diff * diff;
-            if (bidx[p] >= 0) {
+            const bool has1 = active && bidx[p] >= 0;
+            float gx = 0.f, gy = 0.f, gz = 0.f;
+            if (has1) {
                 const float4 s = s_sph[bidx[p]];
                 const float gd = 2.f * wpx * diff;
                 const float inv = gd / bsq[p];
-                atomicAdd(&s_acc[bidx[p] * 3 + 0], -(xg[p] - s.x) * inv);
-                atomicAdd(&s_acc[bidx[p] * 3 + 1], -(yg - s.y) * inv);
-                atomicAdd(&s_acc[bidx[p] * 3 + 2], gd);
+                gx = -(xg[p] - s.x) * inv;
+                gy = -(yg - s.y) * inv;
+                gz = gd;
             }
+            warp_accumulate(acc_w, has1, bidx[p], gx, gy, gz, 0.f, lane);
             // ---- data -> model: distance of the observed point to the nearest sphere surface
-            if (!(z[p] > 99.f)) {
-                float e_best = 3.4e38f, dist_b = 1.f, sgn_b = 0.f;
-                int kb = 0;
+            bool has2 = false;
+            int kb = 0;
+            float hx = 0.f, hy = 0.f, hz = 0.f;
+            if (active && !(z[p] > 99.f)) {
+                // search with the one-instruction approximate square root (the J-sphere loop is what this kernel spends its
+                // time in), then evaluate the winner with the IEEE one: the value and gradient are exact for the sphere found,
+                // and the choice can differ from an exact search only between candidates closer than ~1e-7 relative
+                float e_search = 3.4e38f;
                 for (int k = 0; k < J; ++k) {
                     const float4 s = s_sph[k];
                     const float dx = xg[p] - s.x, dy = yg - s.y, dz = z[p] - s.z;
-                    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
-                    const float sd = dist - s.w;
-                    const float e = fabsf(sd);
-                    if (e < e_best) {
-                        e_best = e; kb = k; dist_b = dist; sgn_b = sd;
-                    }
+                    const float e = fabsf(sqrt_approx(dx * dx + dy * dy + dz * dz) - s.w);
+                    if (e < e_search) { e_search = e; kb = k; }
                 }
+                const float4 sb = s_sph[kb];
+                const float bx = xg[p] - sb.x, by = yg - sb.y, bz = z[p] - sb.z;
+                const float dist_b = sqrtf(bx * bx + by * by + bz * bz);
+                const float sgn_b = dist_b - sb.w;
+                const float e_best = fabsf(sgn_b);
                 l_d2m += fminf(e_best, 50.f);
                 if (e_best > 0.f && e_best <= 50.f && dist_b > 0.f) {
                     const float4 s = s_sph[kb];
                     const float coef = 500.f * wpx * (sgn_b > 0.f ? 1.f : -1.f) / dist_b;   // d|d-r|/dc = sign*(c-P)/dist
-                    atomicAdd(&s_acc[kb * 3 + 0], coef * (s.x - xg[p]));
-                    atomicAdd(&s_acc[kb * 3 + 1], coef * (s.y - yg));
-                    atomicAdd(&s_acc[kb * 3 + 2], coef * (s.z - z[p]));
+                    has2 = true;
+                    hx = coef * (s.x - xg[p]);
+                    hy = coef * (s.y - yg);
+                    hz = coef * (s.z - z[p]);
                 }
             }
+            warp_accumulate(acc_w, has2, kb, hx, hy, hz, 0.f, lane);
         }
     }
     l_m2d = warp_sum(l_m2d);
@@ -194,7 +217,9 @@ __global__ void __launch_bounds__(kThreads) mvproj_main_kernel(
     if (wpx == 0.f) return;
     float* out = reinterpret_cast<float*>(gsph + (size_t)pair * J);
     for (int t = threadIdx.x; t < J * 3; t += kThreads) {
-        const float v = s_acc[t];
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) v += s_acc[w][(t / 3) * 4 + (t % 3)];
         if (v != 0.f) atomicAdd(out + (t / 3) * 4 + (t % 3), v);
     }
     if (threadIdx.x < 2) atomicAdd(&acc[threadIdx.x], (double)s_loss[threadIdx.x] * (double)wpx);

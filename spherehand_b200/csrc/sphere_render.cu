@@ -112,35 +112,6 @@ __global__ void __launch_bounds__(kFwdThreads) sphere_render_fwd_kernel(
     }
 }
 
-// Warp-collective accumulation of one (sphere k, dcx, dcy, dcz, dr) contribution per lane into the warp's PRIVATE table:
-// for every distinct sphere among the participating lanes the contributions are summed with shuffles and the elected lane
-// does a plain read-modify-write -- no shared-memory float atomics (CAS loops, 32-way contended when a tile sits inside one
-// sphere).  `has` may differ per lane; must be called by the whole warp.
-__device__ __forceinline__ void warp_accumulate(float* __restrict__ acc_w, bool has, int k, float ax, float ay, float az, float ar,
-                                                int lane) {
-    unsigned todo = __ballot_sync(0xffffffffu, has);
-    while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int kk = __shfl_sync(0xffffffffu, k, leader);
-        const bool mine = has && k == kk;
-        float a = mine ? ax : 0.f, b = mine ? ay : 0.f, c = mine ? az : 0.f, d = mine ? ar : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-            c += __shfl_xor_sync(0xffffffffu, c, o);
-            d += __shfl_xor_sync(0xffffffffu, d, o);
-        }
-        if (lane == leader) {
-            float4* dst = reinterpret_cast<float4*>(acc_w) + kk;
-            float4 v = *dst;
-            v.x += a; v.y += b; v.z += c; v.w += d;
-            *dst = v;
-        }
-        todo &= ~__ballot_sync(0xffffffffu, mine);
-    }
-}
-
 template <int PX>
 __global__ void __launch_bounds__(kThreads) sphere_render_bwd_kernel(
     const float4* __restrict__ spheres, int J, int H, int W, int tiles_per_block,
