@@ -174,37 +174,56 @@ __global__ void __launch_bounds__(kThreads) mvproj_main_kernel(
                 gz = gd;
             }
             warp_accumulate(acc_w, has1, bidx[p], gx, gy, gz, 0.f, lane);
-            // ---- data -> model: distance of the observed point to the nearest sphere surface
-            bool has2 = false;
-            int kb = 0;
-            float hx = 0.f, hy = 0.f, hz = 0.f;
-            if (active && !(z[p] > 99.f)) {
-                // search with the one-instruction approximate square root (the J-sphere loop is what this kernel spends its
-                // time in), then evaluate the winner with the IEEE one: the value and gradient are exact for the sphere found,
-                // and the choice can differ from an exact search only between candidates closer than ~1e-7 relative
-                float e_search = 3.4e38f;
-                for (int k = 0; k < J; ++k) {
-                    const float4 s = s_sph[k];
-                    const float dx = xg[p] - s.x, dy = yg - s.y, dz = z[p] - s.z;
-                    const float e = fabsf(sqrt_approx(dx * dx + dy * dy + dz * dz) - s.w);
-                    if (e < e_search) { e_search = e; kb = k; }
+        }
+        // ---- data -> model: distance of the observed point to the nearest sphere surface.  The lane's PX pixels
+        // share ONE pass over the J spheres (one broadcast load per sphere, PX independent dependency chains); the search uses
+        // the one-instruction approximate square root (this loop is what the kernel spends its time in), then the winner is
+        // evaluated with the IEEE one: value and gradient are exact for the sphere found, and the choice can differ from an
+        // exact search only between candidates closer than ~1e-7 relative.
+        bool fg[PX];
+        bool any_fg = false;
+        float e_search[PX];
+        int kb[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            fg[p] = active && !(z[p] > 99.f);
+            any_fg |= fg[p];
+            e_search[p] = 3.4e38f;
+            kb[p] = 0;
+        }
+        if (any_fg) {
+            for (int k = 0; k < J; ++k) {
+                const float4 s = s_sph[k];
+                const float dy = yg - s.y;
+                const float dy2 = dy * dy;
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    const float dx = xg[p] - s.x, dz = z[p] - s.z;
+                    const float e = fabsf(sqrt_approx(dx * dx + dy2 + dz * dz) - s.w);
+                    if (e < e_search[p]) { e_search[p] = e; kb[p] = k; }
                 }
-                const float4 sb = s_sph[kb];
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            bool has2 = false;
+            float hx = 0.f, hy = 0.f, hz = 0.f;
+            if (fg[p]) {
+                const float4 sb = s_sph[kb[p]];
                 const float bx = xg[p] - sb.x, by = yg - sb.y, bz = z[p] - sb.z;
                 const float dist_b = sqrtf(bx * bx + by * by + bz * bz);
                 const float sgn_b = dist_b - sb.w;
                 const float e_best = fabsf(sgn_b);
                 l_d2m += fminf(e_best, 50.f);
                 if (e_best > 0.f && e_best <= 50.f && dist_b > 0.f) {
-                    const float4 s = s_sph[kb];
                     const float coef = 500.f * wpx * (sgn_b > 0.f ? 1.f : -1.f) / dist_b;   // d|d-r|/dc = sign*(c-P)/dist
                     has2 = true;
-                    hx = coef * (s.x - xg[p]);
-                    hy = coef * (s.y - yg);
-                    hz = coef * (s.z - z[p]);
+                    hx = coef * (sb.x - xg[p]);
+                    hy = coef * (sb.y - yg);
+                    hz = coef * (sb.z - z[p]);
                 }
             }
-            warp_accumulate(acc_w, has2, kb, hx, hy, hz, 0.f, lane);
+            warp_accumulate(acc_w, has2, kb[p], hx, hy, hz, 0.f, lane);
         }
     }
     l_m2d = warp_sum(l_m2d);
