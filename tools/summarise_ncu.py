@@ -64,3 +64,24 @@ if __name__ == '__main__':
         launches(*sys.argv[2:5])
     else:
         traffic(*sys.argv[2:6])
+
+
+def reps(dst, pairs):
+    """`ncu --set full` reports (.ncu-rep, read with `ncu -i ... --page raw --csv`) -> one CSV row per profiled launch."""
+    import subprocess
+    cols = ['Kernel Name', 'launch__grid_size', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+            'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+            'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+            'launch__registers_per_thread', 'smsp__inst_executed.sum', 'l1tex__m_xbar2l1tex_read_bytes.sum', 'lts__t_sector_hit_rate.pct']
+    with open(dst, 'w', newline='') as f:
+        w = csv.writer(f)
+        w.writerow(['report', 'what'] + cols)
+        for path, what in pairs:
+            out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+            rows = list(csv.reader(out.splitlines()))
+            hdr, units = rows[0], rows[1]
+            unit = dict(zip(hdr, units))
+            for r in rows[2:]:
+                rec = dict(zip(hdr, r))
+                w.writerow([path.split('/')[-1], what] + [(rec.get(c, '')[:70] + (' ' + unit[c] if unit.get(c) and c != 'Kernel Name' else '')).strip()
+                                                           for c in cols])
