@@ -4,17 +4,18 @@ MultiTaskLoss (:147-263) with the reference's constructor arguments, result-dict
 path — what `network/engine.py` of the reference calls unchanged; `spherehand_b200.engine.SelfSupTrainStep` is the same
 arithmetic issued as one static CUDA-graph launch sequence.
 
-Differences, all documented in DESIGN.md: the scale augmentation `ResizeCropImage` (real_aug=True, a per-image Python
-loop in the reference) is a "next" row and raises if enabled in training mode; `temporal_smooth_loss`
-(off by default, cross-iteration state) raises if enabled; `domain_loss` has weight 0 in the reference (:179) and is
-reported as an exact 0 without reading the latents.
+The scale augmentation (real_aug=True, :41-51 / :94-102; a per-image Python loop of `F.interpolate` calls in the reference) runs
+as one batched kernel (`ResizeCropImage`, util_modules.py) with the reference's random draws in the reference's order, so
+the same seeds give the same scales.  Differences, all documented in DESIGN.md: `temporal_smooth_loss` (off by default,
+cross-iteration state) raises if enabled; `domain_loss` has weight 0 in the reference (:179) and is reported as an exact 0
+without reading the latents.
 """
 import torch
 import torch.nn as nn
 
 from .hourglass import create_hourglass_network
 from .pose_vae import PoseVae
-from .util_modules import RecoverXYZCoordinateFromHeatmap
+from .util_modules import RecoverXYZCoordinateFromHeatmap, ResizeCropImage
 from ..mesh.multiview_utility import MultiviewConsistencyLoss, MutualProjectionLoss
 from ..mesh.render import BoneLengthLoss, CollisionLoss
 
@@ -26,12 +27,28 @@ class HeatmapEstimationNetwork(nn.Module):
         self.hg = create_hourglass_network(num_joints * 2, num_stacks)
         self.xyz_recover = RecoverXYZCoordinateFromHeatmap(heatmap_size, heatmap_size, depth_scale)
         self.real_aug = real_aug
-        self.resize_dm = None
+        self.resize_dm = ResizeCropImage() if real_aug else None
 
-    def _check_aug(self):
-        if self.real_aug and self.training:
-            raise NotImplementedError('real_aug (ResizeCropImage scale augmentation, network/util_modules.py:383-424) is not on '
-                                      'the B200 path yet (SURVEY.md §8f-2): construct with real_aug=False or call .eval()')
+    def _augment(self, dms):
+        """The reference's scale augmentation of the real views (:41-51, :94-102), same draws in the same order: one host
+        uniform decides whether to augment at all, then a host draw of the common scale and two device draws of the u / v
+        jitter.  dms [N,H,W] -> (dms, u_scales, v_scales); scales are None when nothing was resized."""
+        if self.resize_dm is None or not self.training:
+            return dms, None, None
+        if torch.rand(1).item() < 0.5:
+            return dms, None, None
+        rnd_scale = torch.rand(dms.shape[0]).to(dms.device) * 0.2 + 0.75
+        u = rnd_scale + torch.rand_like(rnd_scale) * 0.1 - 0.05
+        v = rnd_scale + torch.rand_like(rnd_scale) * 0.1 - 0.05
+        return self.resize_dm(dms, u, v).reshape(dms.shape), u, v
+
+    @staticmethod
+    def _unscale(xyz, u, v):
+        """xyz[:, :, 0] /= u, xyz[:, :, 1] /= v (:60-62, :124-126), out of place (xyz comes from an autograd.Function)."""
+        if u is None:
+            return xyz
+        inv = torch.stack([1.0 / u, 1.0 / v, torch.ones_like(u)], dim=-1).view(-1, 1, 3)
+        return [p * inv for p in xyz]
 
     def _heads(self, output, lo, hi):
         uv = [o[lo:hi, :self.num_joints] for o in output]
@@ -40,14 +57,18 @@ class HeatmapEstimationNetwork(nn.Module):
         return uv, d, xyz
 
     def _foward_real(self, dms):
-        self._check_aug()
         num_real, num_view = dms.shape[0], dms.shape[1]
-        output, _ = self.hg(dms.reshape(num_real * num_view, dms.shape[2], dms.shape[3]))
+        dms, u, v = self._augment(dms.reshape(num_real * num_view, dms.shape[2], dms.shape[3]))
+        output, _ = self.hg(dms)
         uv, d, xyz = self._heads(output, 0, num_real * num_view)
+        xyz = self._unscale(xyz, u, v)
         j = self.num_joints
-        return {'real_uv_hms': [h.reshape(num_real, num_view, j, h.shape[-2], h.shape[-1]) for h in uv],
-                'real_d_hms': [h.reshape(num_real, num_view, j, h.shape[-2], h.shape[-1]) for h in d],
-                'real_xyz': [p.reshape(num_real, num_view, j, 3) for p in xyz]}
+        result = {'real_uv_hms': [h.reshape(num_real, num_view, j, h.shape[-2], h.shape[-1]) for h in uv],
+                  'real_d_hms': [h.reshape(num_real, num_view, j, h.shape[-2], h.shape[-1]) for h in d],
+                  'real_xyz': [p.reshape(num_real, num_view, j, 3) for p in xyz]}
+        if self.resize_dm is not None:
+            result['real_resized_dms'] = dms
+        return result
 
     def _foward_synthetic(self, dms):
         output, _ = self.hg(dms)
@@ -59,17 +80,19 @@ class HeatmapEstimationNetwork(nn.Module):
             return self._foward_real(real_dms)
         if real_dms is None:
             return self._foward_synthetic(synt_dms)
-        self._check_aug()
         num_sync, num_real, num_view = synt_dms.shape[0], real_dms.shape[0], real_dms.shape[1]
-        real_dms = real_dms.reshape(num_real * num_view, real_dms.shape[2], real_dms.shape[3])
+        real_dms, u, v = self._augment(real_dms.reshape(num_real * num_view, real_dms.shape[2], real_dms.shape[3]))
         combined_output, combined_latent = self.hg(torch.cat([synt_dms, real_dms], dim=0))
         j = self.num_joints
         result = {}
         result['synt_uv_hms'], result['synt_d_hms'], result['synt_xyz'] = self._heads(combined_output, 0, num_sync)
         uv, d, xyz = self._heads(combined_output, num_sync, num_sync + num_real * num_view)
+        xyz = self._unscale(xyz, u, v)
         result['real_uv_hms'] = [h.reshape(num_real, num_view, j, h.shape[-2], h.shape[-1]) for h in uv]
         result['real_d_hms'] = [h.reshape(num_real, num_view, j, h.shape[-2], h.shape[-1]) for h in d]
         result['real_xyz'] = [p.reshape(num_real, num_view, j, 3) for p in xyz]
+        if self.resize_dm is not None:
+            result['real_resized_dms'] = real_dms
         result['batch_synt_fea'] = [l[:num_sync] for l in combined_latent]
         result['batch_real_fea'] = [l[num_sync:] for l in combined_latent]
         return result

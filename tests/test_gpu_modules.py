@@ -272,8 +272,28 @@ def test_network_heads_and_full_criterion(hand_model):
     #  between torch-CPU and the kernel; the per-head tests above hold 1e-4 on the reference's fixtures)
     assert rel_err(leaf.grad.cpu(), jo.grad) < 1e-3
     assert rel_err(float(sum(v for k, v in t2.items() if k != 'uv_hm_mean').detach()), float(lo.detach())) < 1e-4
-    with pytest.raises(NotImplementedError):
-        cnc.HeatmapEstimationNetwork(16, 0.01, 41, 1, real_aug=True).to(DEV).train()(real_dms=cu(f['real']) * 0.01)
+    # ---- scale augmentation (real_aug=True, reference :41-62): same draws in the same order as the reference, resized views
+    # from the batched ResizeCropImage kernel, joints divided by the scales
+    aug = cnc.HeatmapEstimationNetwork(16, 0.01, 41, 1, real_aug=True).to(DEV)
+    aug.hg.load_state_dict(oh.det_state_dict(82, 1, seed=7))
+    assert set(aug.state_dict()) == set(net.state_dict())                               # ResizeCropImage holds no state
+    real = cu(f['real']) * 0.01
+    n_img = real.shape[0] * real.shape[1]
+    seed = next(sd for sd in range(100) if torch.manual_seed(sd) and torch.rand(1).item() >= 0.5)
+    torch.manual_seed(seed)
+    out_aug = aug.train()(real_dms=real)
+    torch.manual_seed(seed)
+    assert torch.rand(1).item() >= 0.5
+    rnd = torch.rand(n_img).to(DEV) * 0.2 + 0.75
+    u = rnd + torch.rand_like(rnd) * 0.1 - 0.05
+    v = rnd + torch.rand_like(rnd) * 0.1 - 0.05
+    want = synth.resize_crop(real.reshape(n_img, 64, 64).cpu(), u.cpu(), v.cpu())
+    assert torch.equal(out_aug['real_resized_dms'].cpu(), want)
+    out_ref = aug.eval()(real_dms=want.to(DEV).reshape(real.shape))                      # eval: no augmentation, no division
+    inv = torch.stack([1 / u, 1 / v, torch.ones_like(u)], dim=-1).view(real.shape[0], real.shape[1], 1, 3)
+    assert rel_err(out_aug['real_xyz'][0].detach().cpu(), (out_ref['real_xyz'][0].detach() * inv).cpu()) < 1e-3
+    torch.manual_seed(next(sd for sd in range(100) if torch.manual_seed(sd) and torch.rand(1).item() < 0.5))
+    assert torch.equal(aug.train()(real_dms=real)['real_resized_dms'], real.reshape(n_img, 64, 64))   # the 'no augmentation' draw
 
 
 def test_install_registers_reference_import_names():

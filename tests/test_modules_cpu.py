@@ -63,6 +63,8 @@ def test_module_surfaces_and_state_dict_keys(hand_model):
     net = cnc.HeatmapEstimationNetwork(32, 0.01, 41, 2, real_aug=False)
     ref_keys = set('hg.' + k for k in oh.param_shapes(82, 2)) | {'xyz_recover.u_grid', 'xyz_recover.v_grid'}
     assert set(net.state_dict()) == ref_keys                     # the keys of pretrained/*.pth (SURVEY.md §2.2 assets)
+    aug = cnc.HeatmapEstimationNetwork(32, 0.01, 41, 2)          # real_aug defaults to True like the reference (:28)
+    assert aug.resize_dm is not None and set(aug.state_dict()) == ref_keys
 
     class Constant:
         pass
