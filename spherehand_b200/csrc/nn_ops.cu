@@ -495,22 +495,38 @@ __global__ void __launch_bounds__(kT) upsample_bwd_kernel(const __nv_bfloat16* _
     const int p_end = min((int)(blockIdx.x + 1) * ppb, hw);
     for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
         const int i = pp / w_, j = pp % w_;
+        // the fine rows 2i-1 .. 2i+2 read low row i with weights (0.25, 0.75, 0.75, 0.25); at the image border the clamped tap
+        // folds the missing neighbour's weight into the edge row (1.0 instead of 0.75).  Same for columns: 16 independent loads.
+        float wy[4] = {0.25f, 0.75f, 0.75f, 0.25f}, wx[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+        if (i == 0) { wy[0] = 0.f; wy[1] = 1.f; }
+        if (i == h - 1) { wy[3] = 0.f; wy[2] = 1.f; }
+        if (j == 0) { wx[0] = 0.f; wx[1] = 1.f; }
+        if (j == w_ - 1) { wx[3] = 0.f; wx[2] = 1.f; }
+        const __nv_bfloat16* base = dy + (size_t)n * H * W * C + c0;
+        uint4 raw[16];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int yy = min(max(2 * i - 1 + a, 0), H - 1);          // clamped rows / columns carry weight 0
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int xx = min(max(2 * j - 1 + b, 0), W - 1);
+                raw[a * 4 + b] = *reinterpret_cast<const uint4*>(base + ((size_t)yy * W + xx) * C);
+            }
+        }
         bf8 acc;
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc.v[e] = 0.f;
-        for (int yy = max(2 * i - 2, 0); yy <= min(2 * i + 3, H - 1); ++yy) {
-            int y0, y1; float wy0, wy1;
-            up_taps(yy, h, y0, y1, wy0, wy1);
-            const float wy = (y0 == i ? wy0 : 0.f) + (y1 == i ? wy1 : 0.f);
-            if (wy == 0.f) continue;
-            for (int xx = max(2 * j - 2, 0); xx <= min(2 * j + 3, W - 1); ++xx) {
-                int x0, x1; float wx0, wx1;
-                up_taps(xx, w_, x0, x1, wx0, wx1);
-                const float wx = (x0 == j ? wx0 : 0.f) + (x1 == j ? wx1 : 0.f);
-                if (wx == 0.f) continue;
-                const bf8 g = load8(dy + (((size_t)n * H + yy) * W + xx) * C + c0);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc.v[e] += wy * wx * g.v[e];
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float wgt = wy[a] * wx[b];
+                const uint32_t r[4] = {raw[a * 4 + b].x, raw[a * 4 + b].y, raw[a * 4 + b].z, raw[a * 4 + b].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc.v[2 * e] = fmaf(wgt, __uint_as_float(r[e] << 16), acc.v[2 * e]);
+                    acc.v[2 * e + 1] = fmaf(wgt, __uint_as_float(r[e] & 0xffff0000u), acc.v[2 * e + 1]);
+                }
             }
         }
         store8(dlow + ((size_t)n * hw + pp) * C + c0, acc);

@@ -291,7 +291,14 @@ def test_network_heads_and_full_criterion(hand_model):
     assert torch.equal(out_aug['real_resized_dms'].cpu(), want)
     out_ref = aug.eval()(real_dms=want.to(DEV).reshape(real.shape))                      # eval: no augmentation, no division
     inv = torch.stack([1 / u, 1 / v, torch.ones_like(u)], dim=-1).view(real.shape[0], real.shape[1], 1, 3)
-    assert rel_err(out_aug['real_xyz'][0].detach().cpu(), (out_ref['real_xyz'][0].detach() * inv).cpu()) < 1e-3
+    # two runs of the random-weight network differ by single-ulp bf16 flips that the flat heat-maps amplify (see above), so the
+    # end-to-end comparison is loose (without the division the mean deviation would be ~20 %); the division itself is exact
+    dj = (out_aug['real_xyz'][0].detach() - out_ref['real_xyz'][0].detach() * inv).abs().cpu().numpy()
+    ref_max = float(out_ref['real_xyz'][0].detach().abs().max())
+    assert dj.mean() < 0.03 * ref_max and dj.max() < 0.5 * ref_max
+    p3 = torch.randn(n_img, 41, 3, device=DEV)
+    assert torch.allclose(aug._unscale([p3], u, v)[0], torch.stack([p3[..., 0] / u[:, None], p3[..., 1] / v[:, None], p3[..., 2]], -1), rtol=1e-6)
+    assert aug._unscale([p3], None, None)[0] is p3
     torch.manual_seed(next(sd for sd in range(100) if torch.manual_seed(sd) and torch.rand(1).item() < 0.5))
     assert torch.equal(aug.train()(real_dms=real)['real_resized_dms'], real.reshape(n_img, 64, 64))   # the 'no augmentation' draw
 
