@@ -1,0 +1,136 @@
+"""GPU parity tests of the fused train step (spherehand_b200.engine.SelfSupTrainStep — the product path bench.py times):
+loss terms and parameter gradients against the CPU oracle of the whole step (oracle/full_step.py, itself pinned against
+the reference's own step in tests/test_oracle_golden.py), CUDA-graph replay against the eager launch sequence, the fused
+Adam against torch.optim.Adam, and size-independent properties at BASELINE.json's full size (256 images of 128x128,
+2 stacks).  Tolerances: the hourglass runs bf16 operands / fp32 accumulation, so network-dependent quantities
+are compared at 5e-2; everything that does not pass through the network (Adam arithmetic, term bookkeeping) at 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+if torch.cuda.is_available():
+    from spherehand_b200 import data, ops
+    from spherehand_b200.engine import SelfSupTrainStep, TERM_NAMES
+    from spherehand_b200.model import HandModel
+    from spherehand_b200.network.hourglass import create_hourglass_network
+from oracle import full_step as ofs, hourglass as oh
+
+
+def same_terms(a, b):
+    """Two runs of the same step: fp32 atomics order differs between launches, single-ulp bf16 flips follow, and the flat
+    heat-maps of a random-weight network amplify them: ~0.3 % on the smooth terms, a few % on the two hinge terms (sums of
+    relu over a few active sphere pairs / bones)."""
+    a, b = a.detach().cpu().numpy().astype(np.float64), b.detach().cpu().numpy().astype(np.float64)
+    for i, k in enumerate(TERM_NAMES):
+        tol = 8e-2 if k in ('collision', 'bone_length') else 1.5e-2
+        if abs(a[i] - b[i]) > tol * max(abs(a[i]), abs(b[i])) + 1e-3:
+            return False
+    return True
+
+
+def make_step(hand_model, B, V, Ns, S, stacks, use_graph, seed=7, lr=1e-4):
+    hand = HandModel.from_arrays(hand_model, DEV)
+    vae_sd = {k: torch.from_numpy(v) for k, v in golden('pose_vae').items()}
+    blob = ops.vae_blob_from_state_dict(vae_sd, DEV)
+    net = create_hourglass_network(82, stacks).to(DEV)
+    sd0 = oh.det_state_dict(82, stacks, seed=seed)
+    net.load_state_dict(sd0)
+    step = SelfSupTrainStep(net, hand, blob, B, V, Ns, S, lr=lr, use_graph=use_graph)
+    gen = torch.Generator().manual_seed(1)
+    real, cams, inv = data.synthetic_real_batch(hand, B, V, S, gen)
+    poses = data.random_poses(Ns, gen)
+    step.load_batch(real, cams, inv, poses)
+    torch.manual_seed(3)
+    step.draw_randoms()
+    return step, sd0, vae_sd, dict(real=real.cpu(), cams=cams.cpu(), inv_cams=inv.cpu(), poses=poses.cpu())
+
+
+def test_train_step_terms_and_gradients_vs_oracle(hand_model):
+    B, V, Ns, S, stacks = 2, 3, 2, 64, 1
+    step, sd0, vae_sd, batch = make_step(hand_model, B, V, Ns, S, stacks, use_graph=False)
+    flat0 = step.net._flat.clone()
+    terms = step.step(is_mv=True).cpu().numpy()
+    assert np.isfinite(terms).all()
+    batch.update(scales=step.scales.cpu(), rand_f=step.rand_f.cpu(), noise=step.noise.cpu(), eps=step.vae_eps.cpu())
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    ref, grads, _ = ofs.train_step(sd, stacks, ofs.HandTables(hand_model), vae_sd, batch, S, apply_update=False, round_bf16=True)
+    for k, v in zip(TERM_NAMES, terms):
+        assert abs(v - ref[k]) <= 5e-2 * abs(ref[k]) + 1e-3, (k, float(v), ref[k])
+    assert abs(terms[-1] - terms[:-1].sum()) <= 1e-5 * abs(terms[-1])                      # 'total' is the sum of the 8 terms
+    # parameter gradients (the flat buffer the all-reduce and Adam see) against the oracle's autograd
+    ours, theirs, per = [], [], []
+    for name, p in step.net.named_parameters():
+        g = step.net.grad_view(p).detach().float().cpu().reshape(-1)
+        r = grads[name].reshape(-1)
+        ours.append(g)
+        theirs.append(r)
+        per.append((float(r.norm()), float(g.norm()), name))
+    ours, theirs = torch.cat(ours), torch.cat(theirs)
+    cos = float(torch.dot(ours, theirs) / (ours.norm() * theirs.norm()))
+    ratio = float(ours.norm() / theirs.norm())
+    worst = max(abs(g - r) / r for r, g, _ in sorted(per, reverse=True)[:20])
+    print('gradient cosine %.4f  norm ratio %.4f  worst of the 20 largest parameters %.3f' % (cos, ratio, worst))
+    # random weights give flat heat-maps whose soft-argmax amplifies the bf16 rounding of the network (same effect as in
+    # test_gpu_modules.py): direction and size of the whole gradient are held tightly, single tensors loosely
+    assert cos > 0.95 and abs(ratio - 1) < 0.15 and worst < 0.5
+    # the fused Adam on OUR gradient == torch.optim.Adam(lr, weight_decay=1e-5) on the same gradient (engine.py:95-97 of the reference)
+    p_ref = flat0.clone().requires_grad_(True)
+    p_ref.grad = step.net._flat_grad.clone()
+    torch.optim.Adam([p_ref], lr=1e-4, weight_decay=1e-5).step()
+    assert float((step.net._flat - p_ref.detach()).abs().max()) <= 2e-7                    # one fp32 ulp of a weight; the update is 1e-4
+
+
+def test_graph_replay_equals_eager_over_steps(hand_model):
+    B, V, Ns, S, stacks = 2, 3, 2, 64, 2
+    eager, _, _, _ = make_step(hand_model, B, V, Ns, S, stacks, use_graph=False)
+    graph, _, _, _ = make_step(hand_model, B, V, Ns, S, stacks, use_graph=True)
+    for it in range(3):
+        # same weights and optimiser state at the start of every step (two trajectories drift apart through the noise
+        # described in same_terms; what is compared is one step at a time, multi-view and single-view)
+        eager.net._flat.copy_(graph.net._flat); eager.adam_m.copy_(graph.adam_m); eager.adam_v.copy_(graph.adam_v)
+        eager.step_dev.copy_(graph.step_dev)
+        for st in (eager, graph):
+            torch.manual_seed(100 + it)
+            st.draw_randoms()
+        te = eager.step(is_mv=(it != 1)).clone()
+        tg = graph.step(is_mv=(it != 1)).clone()
+        # same kernels, same inputs; fp32 atomics order differs between runs -> bf16 flips -> small relative differences
+        assert same_terms(te, tg), (it, te.tolist(), tg.tolist())
+    assert graph.launches_per_step and graph.launches_per_step > 100
+    d = (eager.net._flat - graph.net._flat).abs().max()
+    assert float(d) <= 2 * 1e-4 * (1 + 1e-3)             # one Adam step of at most lr each, in either direction
+
+
+def test_full_size_step_properties(hand_model):
+    """BASELINE.json config 3 (B = 64 tuples x 3 views + 64 synthetic poses = 256 images of 128x128, 2 stacks): properties that
+    hold at any size.  (1) every term finite, total = sum; (2) the first Adam step moves no parameter by more than lr;
+    (3) a second replay of the graph on the same inputs with the same weights reproduces the terms; (4) the single-view
+    step (is_mv=False) only changes the two multi-view terms' weighting, not the synthetic / prior terms."""
+    B, V, Ns, S, stacks = 64, 3, 64, 128, 2
+    step, _, _, _ = make_step(hand_model, B, V, Ns, S, stacks, use_graph=True, lr=1e-4)
+    flat0 = step.net._flat.clone()
+    m0, v0, s0 = step.adam_m.clone(), step.adam_v.clone(), step.step_dev.clone()
+    t1 = step.step(is_mv=True).clone()
+    assert torch.isfinite(t1).all()
+    assert abs(float(t1[-1] - t1[:-1].sum())) <= 1e-5 * abs(float(t1[-1]))
+    dp = (step.net._flat - flat0).abs()
+    assert float(dp.max()) <= 1e-4 * (1 + 1e-3) and float(dp.max()) > 0.5e-4
+    assert torch.isfinite(step.net._flat).all()
+    # rewind the weights and optimiser state, replay: same inputs -> same terms (up to atomics order)
+    step.net._flat.copy_(flat0); step.adam_m.copy_(m0); step.adam_v.copy_(v0); step.step_dev.copy_(s0)
+    t2 = step.step(is_mv=True).clone()
+    assert same_terms(t1, t2), (t1.tolist(), t2.tolist())
+    step.net._flat.copy_(flat0); step.adam_m.copy_(m0); step.adam_v.copy_(v0); step.step_dev.copy_(s0)
+    t3 = step.step(is_mv=False).clone()
+    names = list(TERM_NAMES)
+    for k in ('synt_uv', 'synt_d', 'pose_prior', 'uv_hm_mean', 'collision', 'bone_length'):
+        i = names.index(k)
+        tol = 8e-2 if k in ('collision', 'bone_length') else 1.5e-2
+        assert abs(float(t3[i] - t1[i])) <= tol * abs(float(t1[i])) + 1e-3, k
