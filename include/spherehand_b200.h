@@ -107,6 +107,10 @@ int sh_lattice_to_depth(const void* z, int B, int S, int noff, float depth_scale
 /* DepthNoise.forward (network/util_modules.py:60-84) with the three N(0,1) draws supplied by the caller. */
 int sh_depth_noise(const void* dm, const void* nx, const void* ny, const void* nz, int B, int H, int W, float sx,
                    float sy, float sz, void* out, void* stream);
+/* JointAngleDataset.__getitem__ (dataset/joint_angle.py:21-233) for n poses in one launch: pose i consumes its slice of a
+ * pre-drawn uniform stream (u[offsets[i]] ..., at most 44 values) in the reference's order with the reference's fp32 operation
+ * sequence, so the same uniforms give the reference's pose bit for bit.  u fp32, offsets int32 [n], out fp32 [n,26]. */
+int sh_sample_poses(const void* u, const void* offsets, int n, void* out, void* stream);
 /* HeatmapRender.forward + InverseOthographicalProjection (mesh/render.py:226-248, 274-279): uvd float4 [B,J] ->
  * uv_hms, d_hms [B,J,hm,hm], xyz float4 [B,J]. */
 int sh_heatmap_render(const void* uvd, int B, int J, int hm, float sigma, float uv_scale, float depth_scale, float cx,

@@ -267,3 +267,125 @@ SH_EXPORT int sh_heatmap_render(const void* uvd, int B, int J, int hm, float sig
     SH_CHECK_LAUNCH("heatmap_kernel");
     return SH_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ pose sampler
+// JointAngleDataset.__getitem__ (/root/reference/dataset/joint_angle.py:21-233) for n poses in one launch.  The reference
+// draws one pose with ~35 separate `torch.rand(1)` calls and as many tiny tensor ops; here a thread owns a pose and consumes
+// ITS slice of a pre-drawn uniform stream in exactly the reference's order (palm 6, spread + 4 abductions, thumb 4, flexion
+// mode + per-finger draws: between 30 and 44 per pose), with the reference's fp32 operation sequence (explicit _rn
+// intrinsics: no FMA contraction), so that fed the same uniforms it is bit-identical to the reference.  offsets[i] is the
+// index of pose i's first uniform (sequential stream: the host walks the mode draws; independent streams: i * 48).
+namespace {
+
+struct USrc {
+    const float* u;
+    int p;
+    __device__ __forceinline__ float next() { return u[p++]; }
+};
+constexpr float kPiF = 3.14159274101257324f;              // float32(math.pi): the scalar is cast to the tensor's dtype
+
+__device__ __forceinline__ float ja_deg(float a) { return __fdiv_rn(__fmul_rn(a, kPiF), 180.f); }       // a * pi / 180
+// curr_flex = (rand * 30 + base) * pi / 180 + (rand * 20 - 10) * pi / 180
+__device__ __forceinline__ float ja_curr(USrc& s, float base) {
+    const float a = ja_deg(__fadd_rn(__fmul_rn(s.next(), 30.f), base));
+    const float b = ja_deg(__fsub_rn(__fmul_rn(s.next(), 20.f), 10.f));
+    return __fadd_rn(a, b);
+}
+// the three "curled" finger shapes (:42-103) differ only in the additive constants of their three flexion draws
+__device__ __forceinline__ void ja_curled(USrc& s, float b1, float b2, float b3, float* f) {
+    float f1 = -0.2f, f2 = -0.4f, f3 = -0.34f;
+    float c = ja_curr(s, b1);
+    f1 = __fadd_rn(f1, c);                                // 1.0 * curr_flex
+    f2 = __fadd_rn(f2, __fmul_rn(0.2f, c));
+    c = ja_curr(s, b2);
+    f1 = __fadd_rn(f1, __fmul_rn(0.2f, c));
+    f2 = __fadd_rn(f2, c);
+    f3 = __fadd_rn(f3, __fmul_rn(0.7f, c));
+    c = ja_curr(s, b3);
+    f2 = __fadd_rn(f2, __fmul_rn(0.2f, c));
+    f3 = __fadd_rn(f3, c);
+    f[0] = f1; f[1] = f2; f[2] = f3;
+}
+// finger shape by index: 0 straight, 1 open, 2 half open, 3 pinching, 4 closed (_set_rand_flex's numbering, :145-158)
+__device__ __forceinline__ void ja_finger(USrc& s, int shape, float* f) {
+    if (shape == 0) {
+        f[0] = __fsub_rn(__fmul_rn(s.next(), 0.25f), 0.25f);
+        f[1] = __fsub_rn(__fmul_rn(s.next(), 0.4f), 0.4f);
+        f[2] = __fsub_rn(__fmul_rn(s.next(), 0.34f), 0.34f);
+    } else if (shape == 1) {
+        f[0] = __fsub_rn(__fmul_rn(s.next(), 0.25f), 0.1f);
+        f[1] = __fsub_rn(__fmul_rn(s.next(), 0.4f), 0.1f);
+        f[2] = __fsub_rn(__fmul_rn(s.next(), 0.34f), 0.1f);
+    } else if (shape == 2) {
+        ja_curled(s, 0.f, 60.f, 60.f, f);                 // (rand*30)*pi/180 == (rand*30 + 0)*pi/180 bit for bit
+    } else if (shape == 3) {
+        ja_curled(s, 60.f, 5.f, 5.f, f);
+    } else {
+        ja_curled(s, 60.f, 60.f, 60.f, f);
+    }
+}
+__device__ __forceinline__ int ja_mode(USrc& s, float n) { return (int)__fmul_rn(s.next(), n); }        // int(torch.rand(1) * n)
+
+__global__ void pose_sample_kernel(const float* __restrict__ u, const int* __restrict__ offsets, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    USrc s{u, offsets[i]};
+    float* p = out + (size_t)i * 26;
+    // _set_palm (:21-29)
+    p[0] = __fsub_rn(__fmul_rn(s.next(), 6.28f), 3.14f);
+    p[1] = __fmul_rn(-s.next(), 3.14f);
+    p[2] = __fsub_rn(__fmul_rn(s.next(), 6.28f), 3.14f);
+    p[3] = __fsub_rn(__fmul_rn(s.next(), 30.f), 15.f);
+    p[4] = __fsub_rn(__fmul_rn(s.next(), 30.f), 15.f);
+    p[5] = __fsub_rn(__fmul_rn(s.next(), 50.f), 35.f);
+    // _set_abduct (:31-39): index, middle, ring, pinky
+    const float spread = __fdiv_rn(__fsub_rn(s.next(), 0.35f), 1.55f);
+    const float ka[4] = {1.55f, 0.75f, -0.75f, -2.2f};
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        const float r = ja_deg(__fsub_rn(__fmul_rn(s.next(), 10.f), 5.f));
+        p[6 + 4 * f] = __fmul_rn(ka[f], __fadd_rn(spread, r));
+    }
+    // _set_thumb (:117-128) -> parameter[22:26] = (abduct, flex, 0.25 flex, flex_3)
+    {
+        const float sel = s.next();
+        const float v = s.next();
+        const float flex = sel < 0.5f ? __fsub_rn(__fmul_rn(v, 0.35f), 0.25f) : __fadd_rn(__fmul_rn(v, 0.6f), 0.1f);
+        const float f3 = __fsub_rn(__fmul_rn(s.next(), 2.f), 1.7f);
+        p[22] = __fsub_rn(s.next(), 0.5f);
+        p[23] = flex;
+        p[24] = __fmul_rn(0.25f, flex);
+        p[25] = f3;
+    }
+    // _set_flex (:160-214).  Per-finger rule: >= 0 a fixed shape, -1 rand_open (:130-137), -2 rand_close (:139-144), -3 rand_flex.
+    // The second `mode == 8` branch of the reference (index & pinky open) is unreachable; mode 10 (rand*10 rounding up to 10.0)
+    // leaves `flex` undefined there and is mapped to 9 here.
+    const int mode = min(ja_mode(s, 10.f), 9);
+    int rule[4];
+    if (mode <= 4) { rule[0] = rule[1] = rule[2] = rule[3] = mode; }
+    else if (mode == 5) { rule[0] = -1; rule[1] = -2; rule[2] = -2; rule[3] = -2; }
+    else if (mode == 6) { rule[0] = -2; rule[1] = -2; rule[2] = -2; rule[3] = -1; }
+    else if (mode == 7) { rule[0] = -1; rule[1] = -1; rule[2] = -2; rule[3] = -2; }
+    else if (mode == 8) { rule[0] = -2; rule[1] = -1; rule[2] = -1; rule[3] = -1; }
+    else { rule[0] = rule[1] = rule[2] = rule[3] = -3; }
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        int shape = rule[f];
+        if (shape == -1) shape = min(ja_mode(s, 3.f), 2);                 // straight / open / half open
+        else if (shape == -2) shape = 3 + min(ja_mode(s, 2.f), 1);        // pinching / closed
+        else if (shape == -3) shape = min(ja_mode(s, 5.f), 4);
+        ja_finger(s, shape, p + 7 + 4 * f);
+    }
+}
+
+}  // namespace
+
+// u: fp32 uniforms in [0,1); offsets int32 [n] (first uniform of every pose; a pose reads at most 44); out fp32 [n,26]
+SH_EXPORT int sh_sample_poses(const void* u, const void* offsets, int n, void* out, void* stream) {
+    SH_REQUIRE(n >= 0, "sh_sample_poses: bad n");
+    if (n == 0) return SH_OK;
+    SH_REQUIRE(u && offsets && out, "sh_sample_poses: null pointer");
+    pose_sample_kernel<<<sh_div_up(n, 64), 64, 0, (cudaStream_t)stream>>>((const float*)u, (const int*)offsets, n, (float*)out);
+    SH_CHECK_LAUNCH("pose_sample_kernel");
+    return SH_OK;
+}

@@ -89,6 +89,12 @@ class SelfSupTrainStep:
         self.poses.copy_(pose_parameters, non_blocking=non_blocking)
         return real_dms.numel() * 4 + 2 * camera_poses.numel() * 4 + pose_parameters.numel() * 4
 
+    def sample_poses(self, generator=None, sequential=True):
+        """Fill the synthetic-branch poses on the device with the batched JointAngleDataset sampler (dataset/joint_angle.py of the
+        reference: what its DataLoader workers draw one `torch.rand(1)` at a time) instead of copying them from the host."""
+        from .dataset.joint_angle import JointAngleDataset
+        self.poses.copy_(JointAngleDataset(self.dev).sample_batch(self.Ns, generator, sequential))
+
     def draw_randoms(self, generator=None):
         """The step's random draws, in the reference's order: RandScale x,y,z (pointTransformation.py:140-142),
         rand_f_ratio (util_modules.py:107), DepthNoise shift_x, shift_y, z (util_modules.py:64,69,83), VAE eps per stack

@@ -367,6 +367,14 @@ def resize_crop(depth_maps, u_scales, v_scales):
     return out
 
 
+def sample_poses(u, offsets):
+    """u: fp32 uniforms (any shape, contiguous), offsets int32 [n] -> poses [n,26] (sh_sample_poses)."""
+    n = offsets.numel()
+    out = torch.empty((n, 26), device=u.device, dtype=torch.float32)
+    _call('sh_sample_poses', _chk(u, name='u'), _chk(offsets, torch.int32, 'offsets'), n, out.data_ptr(), _stream())
+    return out
+
+
 def scale(x, s, out):
     _call('sh_scale', _chk(x, name='x'), float(s), x.numel(), _chk(out, name='out'), _stream())
     return out

@@ -28,9 +28,12 @@ def same_terms(a, b):
     heat-maps of a random-weight network amplify them: ~0.3 % on the smooth terms, a few % on the two hinge terms (sums of
     relu over a few active sphere pairs / bones)."""
     a, b = a.detach().cpu().numpy().astype(np.float64), b.detach().cpu().numpy().astype(np.float64)
+    total = max(abs(a[-1]), abs(b[-1]))
     for i, k in enumerate(TERM_NAMES):
-        tol = 8e-2 if k in ('collision', 'bone_length') else 1.5e-2
-        if abs(a[i] - b[i]) > tol * max(abs(a[i]), abs(b[i])) + 1e-3:
+        hinge = k in ('collision', 'bone_length')
+        # a hinge term can switch single pairs on or off: its absolute slack is tied to the size of the whole loss
+        if abs(a[i] - b[i]) > (8e-2 if hinge else 1.5e-2) * max(abs(a[i]), abs(b[i])) + (2e-3 * total if hinge else 1e-3):
+            print('term', k, a[i], b[i])
             return False
     return True
 
@@ -132,5 +135,5 @@ def test_full_size_step_properties(hand_model):
     names = list(TERM_NAMES)
     for k in ('synt_uv', 'synt_d', 'pose_prior', 'uv_hm_mean', 'collision', 'bone_length'):
         i = names.index(k)
-        tol = 8e-2 if k in ('collision', 'bone_length') else 1.5e-2
-        assert abs(float(t3[i] - t1[i])) <= tol * abs(float(t1[i])) + 1e-3, k
+        hinge = k in ('collision', 'bone_length')
+        assert abs(float(t3[i] - t1[i])) <= (8e-2 if hinge else 1.5e-2) * abs(float(t1[i])) + (2e-3 * abs(float(t1[-1])) if hinge else 1e-3), k

@@ -194,6 +194,31 @@ def test_resize_crop_image_against_golden_and_oracle():
         rc(torch.rand(2, 8, 8), torch.ones(2), torch.ones(2))                      # host tensors: no CPU fallback
 
 
+def test_joint_angle_dataset_against_reference_fixture():
+    """The batched pose sampler: same generator state -> the reference's poses bit for bit (256 consecutive `__getitem__`
+    results of the unmodified reference), generator left where the reference leaves it; independent-stream mode against the
+    oracle restatement; the poses drive the FK kernel unchanged."""
+    from spherehand_b200.dataset import joint_angle as ja
+    from oracle import poses as oposes
+    g = golden('joint_angle')
+    n = g['poses'].shape[0]
+    ds = ja.JointAngleDataset()
+    assert len(ds) == 400000 and ds.num_parameter == 26
+    torch.manual_seed(int(g['seed']))
+    p = ds.sample_batch(n)
+    assert p.is_cuda and np.array_equal(p.cpu().numpy(), g['poses'])
+    assert np.array_equal(torch.rand(4).numpy(), g['after'])
+    torch.manual_seed(int(g['seed']))
+    assert np.array_equal(ds[0].cpu().numpy(), g['poses'][0]) and np.array_equal(ds[1].cpu().numpy(), g['poses'][1])
+    gen = torch.Generator().manual_seed(5)
+    q = ds.sample_batch(1000, generator=gen, sequential=False).cpu().numpy()
+    u = torch.rand(1000 * ja.MAX_UNIFORMS, generator=torch.Generator().manual_seed(5)).numpy()
+    for i in (0, 1, 499, 999):
+        assert np.array_equal(q[i], oposes.joint_angle_getitem(oposes._Stream(u, i * ja.MAX_UNIFORMS)))
+    assert np.isfinite(q).all() and q[:, 1].max() <= 0 and q[:, 1].min() >= -3.1400001
+    assert ds.sample_batch(0).shape == (0, 26)
+
+
 def test_network_heads_and_full_criterion(hand_model):
     # soft-argmax head through autograd
     g = golden('softargmax')

@@ -77,6 +77,22 @@ def test_module_surfaces_and_state_dict_keys(hand_model):
         cnc.MultiTaskLoss(True, True, True, True, False, True, True, Constant())
 
 
+def test_joint_angle_host_walk_and_generator_position():
+    """Host side of the batched pose sampler (spherehand_b200/dataset/joint_angle.py): the integer walk over the mode draws
+    finds the same pose boundaries as the oracle restatement, and the generator is left exactly where n consecutive
+    `__getitem__` calls of the reference leave it (fixture value `after`)."""
+    from spherehand_b200.dataset import joint_angle as ja
+    from oracle import poses as oposes
+    g = golden('joint_angle')
+    n = g['poses'].shape[0]
+    _, offs, used = oposes.joint_angle_batch(g['u'], n)
+    o, e = ja.sequential_offsets(g['u'])
+    assert np.array_equal(o[:n], offs) and int(e[n - 1]) == used and ja.MAX_UNIFORMS == 44
+    with pytest.raises(RuntimeError):
+        ja.JointAngleDataset(device='cpu')
+    assert len(ja.JointAngleDataset.__mro__) and ja.JointAngleDataset.INDEX == 6 and ja.JointAngleDataset.THUMB == 22
+
+
 def test_no_cpu_fallback_anywhere(hand_model):
     """Every forward on CPU tensors raises (CHECK_CUDA of the reference shim, depth_rasterization_cuda.cpp:11-13): the
     product path must never silently compute on the host."""
@@ -105,12 +121,12 @@ def test_install_table():
     names = spherehand_b200.install()
     try:
         assert {'depth_rasterization', 'mesh.render', 'mesh.cuda_kernel', 'mesh.multiview_utility', 'mesh.kinematicsTransformation',
-                'mesh.pointTransformation', 'network.hourglass', 'network.create_network_and_criterion'} <= set(names)
+                'mesh.pointTransformation', 'network.hourglass', 'network.create_network_and_criterion', 'dataset.joint_angle'} <= set(names)
         import depth_rasterization
         assert callable(depth_rasterization.forward)
     finally:
         for k in set(sys.modules) - before:
-            if k.split('.')[0] in ('mesh', 'network', 'depth_rasterization'):
+            if k.split('.')[0] in ('mesh', 'network', 'depth_rasterization', 'dataset'):
                 sys.modules.pop(k, None)
 
 
