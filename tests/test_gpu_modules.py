@@ -219,6 +219,34 @@ def test_joint_angle_dataset_against_reference_fixture():
     assert ds.sample_batch(0).shape == (0, 26)
 
 
+def test_shard_batch_loader_prefetch():
+    """ShardBatchLoader over the committed shards: device batches equal direct indexing (sequential and seeded-shuffle order),
+    staging buffers are pinned, batches stay valid while the next one is prefetched, several epochs reuse the buffers."""
+    import os
+    from spherehand_b200.dataset import nyu_dataset as nd
+    ds = nd.create_nyu_dataset(os.path.join(os.path.dirname(__file__), 'golden', 'shard'))
+    ld = nd.ShardBatchLoader(ds, 3, device=DEV, shuffle=False)
+    assert len(ld) == 2 and all(h.is_pinned() for slot in ld._host for h in slot)
+    for epoch in range(2):
+        seen = []
+        for b, (dm, jp, cp, icp) in enumerate(ld):
+            assert dm.is_cuda and dm.shape == (3, 3, 16, 16) and cp.shape == (3, 3, 4, 4)
+            seen.append((dm, jp, cp, icp))                       # keep the previous batch alive across the next request
+            for k in range(3):
+                want = ds[b * 3 + k]
+                for got, w in zip((dm, jp, cp, icp), want):
+                    assert np.array_equal(got[k].cpu().numpy(), np.asarray(w, np.float32))
+        assert len(seen) == 2
+        assert np.array_equal(seen[0][0][0].cpu().numpy(), np.asarray(ds[0][0]))       # batch 0 still intact after batch 1 arrived
+    gen = torch.Generator().manual_seed(3)
+    order = torch.randperm(len(ds), generator=torch.Generator().manual_seed(3)).tolist()
+    for b, (dm, jp, cp, icp) in enumerate(nd.ShardBatchLoader(ds, 4, device=DEV, shuffle=True, generator=gen)):
+        for k in range(4):
+            assert np.array_equal(icp[k].cpu().numpy(), ds[order[b * 4 + k]][3].astype(np.float32))
+    with pytest.raises(ValueError):
+        nd.ShardBatchLoader(ds, 9, device=DEV)
+
+
 def test_network_heads_and_full_criterion(hand_model):
     # soft-argmax head through autograd
     g = golden('softargmax')

@@ -1,5 +1,7 @@
 """CPU-side checks of the drop-in module surfaces (no kernel runs): constructor arguments, registered buffers /
 state_dict keys the reference's checkpoints and callers rely on, host-side tables, and the no-CPU-fallback rule."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -91,6 +93,31 @@ def test_joint_angle_host_walk_and_generator_position():
     with pytest.raises(RuntimeError):
         ja.JointAngleDataset(device='cpu')
     assert len(ja.JointAngleDataset.__mro__) and ja.JointAngleDataset.INDEX == 6 and ja.JointAngleDataset.THUMB == 22
+
+
+def test_npy_shard_reader_and_writer(tmp_path):
+    """dataset/nyu_dataset.py mirror: the committed shards (tests/golden/shard, the reference's on-disk format) read item by item
+    like the UNMODIFIED reference reader did (tests/golden/shard_items.npz, oracle/make_golden_shard.py), inverse camera poses
+    included bit for bit; the writer reproduces the shard files byte for byte."""
+    import filecmp
+    from spherehand_b200.dataset import nyu_dataset as nd
+    shard_dir = os.path.join(os.path.dirname(__file__), 'golden', 'shard')
+    g = golden('shard_items')
+    ds = nd.create_nyu_dataset(shard_dir)
+    assert len(ds) == int(g['n']) == 8 and len(ds.datasets) == 2
+    for i in range(len(ds)):
+        dm, jp, cp, icp = ds[i]
+        assert dm.dtype == np.float32 and dm.shape == (3, 16, 16)
+        for a, k in ((dm, 'dm'), (jp, 'jp'), (cp, 'cp'), (icp, 'icp')):
+            assert np.array_equal(a, g['%s%d' % (k, i)])
+    one = nd.NpyDataset(os.path.join(shard_dir, 'mv_data_1'), transform=lambda dm, jp, cp, icp: (dm.sum(), jp.shape))
+    assert len(one) == 3 and one[2][1] == (3, 36, 3)
+    src = nd.NpyDataset(os.path.join(shard_dir, 'mv_data_0'))
+    nd.write_npy_shard(str(tmp_path), 'mv_data_0', np.asarray(src.dms), src.joint_poses, src.camera_poses)
+    for suffix in ('_dms.bat', '_joint_poses.npy', '_camera_poses.npy', '_shape.pkl'):
+        assert filecmp.cmp(os.path.join(shard_dir, 'mv_data_0' + suffix), str(tmp_path / ('mv_data_0' + suffix)), shallow=False), suffix
+    with pytest.raises(RuntimeError):
+        nd.ShardBatchLoader(ds, 2, device='cpu')
 
 
 def test_no_cpu_fallback_anywhere(hand_model):
