@@ -71,6 +71,7 @@ class SelfSupTrainStep:
         net.flatten_parameters()
         self.adam_m = torch.zeros_like(net._flat)
         self.adam_v = torch.zeros_like(net._flat)
+        self.lr = float(lr)
         self.lr_dev = torch.tensor([lr], **f32)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.projected_dms = None
@@ -79,6 +80,7 @@ class SelfSupTrainStep:
 
     # ------------------------------------------------------------------ host-side plumbing
     def set_lr(self, lr):
+        self.lr = float(lr)
         self.lr_dev.fill_(lr)
 
     def load_batch(self, real_dms, camera_poses, inv_camera_poses, pose_parameters, non_blocking=True):
@@ -209,6 +211,54 @@ class SelfSupTrainStep:
         self._allreduce()
         g_opt.replay()
         return self.terms
+
+    # ------------------------------------------------------------------ checkpoints (reference format)
+    def _flat_views(self, flat):
+        net = self.net
+        return [flat[off:off + n].view(p.shape) for p in net.parameters() for off, n in (net._offsets[id(p)],)]
+
+    def checkpoint(self, epoch):
+        """The dict `Engine.save_model` writes (network/engine.py:437-443): {'epoch', 'network_state_dict', 'optimizer_state_dict'}.
+        `network_state_dict` has the keys of the reference's HeatmapEstimationNetwork (`hg.*` + the soft-argmax grids);
+        `optimizer_state_dict` is produced by a real torch.optim.Adam holding views of the flat moment buffers, so it is in
+        the installed torch's own format and `torch.optim.Adam.load_state_dict` of the reference takes it unchanged."""
+        net = self.net
+        sd = {'hg.' + k: v.detach().clone() for k, v in net.state_dict().items()}
+        hm = self.hm
+        v_grid, u_grid = torch.meshgrid(torch.arange(hm, dtype=torch.float32), torch.arange(hm, dtype=torch.float32), indexing='ij')
+        sd['xyz_recover.u_grid'] = u_grid.reshape(1, 1, hm, hm).to(self.dev)
+        sd['xyz_recover.v_grid'] = v_grid.reshape(1, 1, hm, hm).to(self.dev)
+        params = list(net.parameters())
+        opt = torch.optim.Adam(params, lr=self.lr, betas=self.betas, eps=self.eps_adam, weight_decay=self.weight_decay)
+        step = float(self.step_dev.item())
+        if step > 0:
+            for p, m, v in zip(params, self._flat_views(self.adam_m), self._flat_views(self.adam_v)):
+                opt.state[p] = {'step': torch.tensor(step), 'exp_avg': m.detach().clone(), 'exp_avg_sq': v.detach().clone()}
+        return {'epoch': epoch, 'network_state_dict': sd, 'optimizer_state_dict': opt.state_dict()}
+
+    def load_checkpoint(self, check_point, load_optimizer=True):
+        """`Engine.load_model` (network/engine.py:445-459) for the fused step: weights into the flat buffer, and (for a numbered
+        checkpoint) Adam's moments, step count and learning rate into the device-side optimiser state."""
+        net = self.net
+        sd = {k[3:]: v for k, v in check_point['network_state_dict'].items() if k.startswith('hg.')}
+        net.load_state_dict(sd)
+        net.flatten_parameters()
+        if not load_optimizer:
+            return
+        params = list(net.parameters())
+        opt = torch.optim.Adam(params, lr=self.lr, betas=self.betas, eps=self.eps_adam, weight_decay=self.weight_decay)
+        opt.load_state_dict(check_point['optimizer_state_dict'])
+        self.adam_m.zero_(); self.adam_v.zero_()
+        steps = set()
+        for p, m, v in zip(params, self._flat_views(self.adam_m), self._flat_views(self.adam_v)):
+            st = opt.state.get(p)
+            if st:
+                m.copy_(st['exp_avg']); v.copy_(st['exp_avg_sq'])
+                steps.add(int(float(st['step'])))
+        if len(steps) > 1:
+            raise ValueError('checkpoint holds different Adam step counts per parameter; the fused optimiser keeps one')
+        self.step_dev.fill_(steps.pop() if steps else 0)
+        self.set_lr(opt.param_groups[0]['lr'])
 
     def loss_dict(self):
         t = self.terms.tolist()

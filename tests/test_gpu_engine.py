@@ -137,3 +137,39 @@ def test_full_size_step_properties(hand_model):
         i = names.index(k)
         hinge = k in ('collision', 'bone_length')
         assert abs(float(t3[i] - t1[i])) <= (8e-2 if hinge else 1.5e-2) * abs(float(t1[i])) + (2e-3 * abs(float(t1[-1])) if hinge else 1e-3), k
+
+
+def test_checkpoint_roundtrip_in_the_reference_format(hand_model, tmp_path):
+    """SelfSupTrainStep.checkpoint / load_checkpoint speak `Engine.save_model` / `load_model`'s format (network/engine.py:437-459):
+    after two steps the dict survives torch.save / torch.load, a stock torch.optim.Adam over a fresh copy of the network loads
+    its optimiser part unchanged (what the reference would do), and a second fused step object restored from it holds the same
+    weights, moments, step count and learning rate bit for bit."""
+    B, V, Ns, S, stacks = 2, 3, 2, 64, 1
+    a, _, _, _ = make_step(hand_model, B, V, Ns, S, stacks, use_graph=False, lr=3e-4)
+    for _ in range(2):
+        a.step(is_mv=True)
+    ck = a.checkpoint(epoch=7)
+    path = str(tmp_path / 'model_7.pth')
+    torch.save(ck, path)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {'epoch', 'network_state_dict', 'optimizer_state_dict'} and ck['epoch'] == 7
+    keys = set(ck['network_state_dict'])
+    assert {'xyz_recover.u_grid', 'xyz_recover.v_grid'} <= keys and all(k.startswith('hg.') or k.startswith('xyz_recover.') for k in keys)
+    assert ck['network_state_dict']['xyz_recover.u_grid'][0, 0, 3, 5] == 5 and ck['network_state_dict']['xyz_recover.v_grid'][0, 0, 3, 5] == 3
+    # reference side: stock Adam over a stock copy of the parameters
+    ref_net = create_hourglass_network(82, stacks).to(DEV)
+    ref_net.load_state_dict({k[3:]: v for k, v in ck['network_state_dict'].items() if k.startswith('hg.')})
+    ref_opt = torch.optim.Adam(ref_net.parameters(), lr=1.0, weight_decay=1e-5)
+    ref_opt.load_state_dict(ck['optimizer_state_dict'])
+    assert ref_opt.param_groups[0]['lr'] == 3e-4 and ref_opt.param_groups[0]['weight_decay'] == 1e-5
+    p0 = next(iter(ref_net.parameters()))
+    assert int(float(ref_opt.state[p0]['step'])) == 2 and ref_opt.state[p0]['exp_avg'].shape == p0.shape
+    # fused side: a new step object restored from the checkpoint
+    b, _, _, _ = make_step(hand_model, B, V, Ns, S, stacks, use_graph=False, seed=99, lr=1e-4)
+    assert not torch.equal(a.net._flat, b.net._flat)
+    b.load_checkpoint(ck)
+    assert torch.equal(a.net._flat, b.net._flat) and torch.equal(a.adam_m, b.adam_m) and torch.equal(a.adam_v, b.adam_v)
+    assert int(b.step_dev.item()) == 2 and b.lr == 3e-4 and abs(float(b.lr_dev.item()) - 3e-4) < 1e-9
+    tb = b.step(is_mv=True).clone()
+    ta = a.step(is_mv=True).clone()
+    assert same_terms(ta, tb)
