@@ -107,6 +107,12 @@ int sh_lattice_to_depth(const void* z, int B, int S, int noff, float depth_scale
 /* DepthNoise.forward (network/util_modules.py:60-84) with the three N(0,1) draws supplied by the caller. */
 int sh_depth_noise(const void* dm, const void* nx, const void* ny, const void* nz, int B, int H, int W, float sx,
                    float sy, float sz, void* out, void* stream);
+/* PoseDenoiser.forward in eval mode (network/pose_denoiser.py:56-73): out = fea with the out_idx entries replaced by
+ * MLP(fea[:, in_idx] * scale) / scale.  blob: sh_pose_denoiser_blob_floats(n_in, n_out) floats = W1^T [n_in,256], b1, gamma1,
+ * beta1, W2^T [256,256], b2, gamma2, beta2, W3^T [256,n_out], b3.  fea, out fp32 [M,n_fea]; indices int32. */
+size_t sh_pose_denoiser_blob_floats(int n_in, int n_out);
+int sh_pose_denoiser_fwd(const void* fea, const void* in_idx, const void* out_idx, const void* blob, int M, int n_fea, int n_in,
+                         int n_out, float scale, void* out, void* stream);
 /* JointAngleDataset.__getitem__ (dataset/joint_angle.py:21-233) for n poses in one launch: pose i consumes its slice of a
  * pre-drawn uniform stream (u[offsets[i]] ..., at most 44 values) in the reference's order with the reference's fp32 operation
  * sequence, so the same uniforms give the reference's pose bit for bit.  u fp32, offsets int32 [n], out fp32 [n,26]. */

@@ -183,3 +183,20 @@ def soft_argmax_xyz(uv_hms, d_hms, depth_scale=0.01):
     y = (v - h / 2) / (h / 300.0)
     z = d * (1.0 / depth_scale)
     return torch.stack([x, y, z], dim=-1)
+
+
+def pose_denoiser_forward(sd, fea, input_indices, output_indices, scale_factor=0.01):
+    """PoseDenoiser.forward in eval mode, network/pose_denoiser.py:56-73, statement by statement (torch fp32 CPU).
+    sd: state_dict with the reference's keys (network.0/1/3/4/6.*)."""
+    import torch.nn.functional as F
+    is_skel = fea.ndimension() == 3
+    shape = fea.shape
+    if is_skel:
+        fea = fea.reshape(shape[0], -1)
+    x = fea[:, input_indices] * scale_factor
+    x = F.relu(F.group_norm(F.linear(x, sd['network.0.weight'], sd['network.0.bias']), 16, sd['network.1.weight'], sd['network.1.bias']))
+    x = F.relu(F.group_norm(F.linear(x, sd['network.3.weight'], sd['network.3.bias']), 16, sd['network.4.weight'], sd['network.4.bias']))
+    y = F.linear(x, sd['network.6.weight'], sd['network.6.bias']) / scale_factor
+    out = fea.clone()
+    out[:, output_indices] = y
+    return out.reshape(shape) if is_skel else out

@@ -12,7 +12,7 @@ def install():
     reference (or user code written against them) run on the new path unchanged:
         depth_rasterization, mesh.cuda_kernel, mesh.render, mesh.multiview_utility, mesh.kinematicsTransformation,
         mesh.pointTransformation, network.hourglass, network.create_network_and_criterion, network.util_modules,
-        network.pose_vae, dataset.joint_angle, dataset.nyu_dataset.
+        network.pose_vae, network.pose_denoiser, dataset.joint_angle, dataset.nyu_dataset.
     Only names that are not already imported are registered (an already-imported reference module is left alone)."""
     import importlib
     from . import depth_rasterization
@@ -30,6 +30,7 @@ def install():
         'network.create_network_and_criterion': importlib.import_module('.network.create_network_and_criterion', __name__),
         'network.util_modules': importlib.import_module('.network.util_modules', __name__),
         'network.pose_vae': importlib.import_module('.network.pose_vae', __name__),
+        'network.pose_denoiser': importlib.import_module('.network.pose_denoiser', __name__),
         'dataset': importlib.import_module('.dataset', __name__),
         'dataset.joint_angle': importlib.import_module('.dataset.joint_angle', __name__),
         'dataset.nyu_dataset': importlib.import_module('.dataset.nyu_dataset', __name__),

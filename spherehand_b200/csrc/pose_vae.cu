@@ -264,3 +264,73 @@ SH_EXPORT int sh_vae_prior_fwdbwd(const void* x, const void* eps, const void* we
     SH_CHECK_LAUNCH("vae_finish_kernel");
     return SH_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ PoseDenoiser (eval)
+// PoseDenoiser.forward in eval mode (/root/reference/network/pose_denoiser.py:56-73): gather 112 of the 123 joint coordinates,
+// x0.01, Linear(112,256)+GroupNorm(16,256)+ReLU, Linear(256,256)+GroupNorm+ReLU, Linear(256,33), /0.01, scatter into a copy of
+// the input.  The reference runs 3 GEMMs, 2 GroupNorms and ~10 index / elementwise kernels for a handful of rows; here a CTA
+// owns 4 rows and keeps every activation in shared memory (same dense / GroupNorm helpers as the VAE prior above).
+namespace {
+
+struct DenWeights {
+    const float *w1t, *b1, *g1, *be1;      // n_in -> 256  (W^T [in,out])
+    const float *w2t, *b2, *g2, *be2;      // 256  -> 256
+    const float *w3t, *b3;                 // 256  -> n_out
+};
+
+__global__ void __launch_bounds__(kThreads) pose_denoiser_kernel(const float* __restrict__ fea, const int* __restrict__ in_idx,
+                                                                 const int* __restrict__ out_idx, const DenWeights W, int M, int n_fea,
+                                                                 int n_in, int n_out, float scale, float* __restrict__ out) {
+    __shared__ float s_x[RB * HID];        // gathered, scaled input rows (n_in <= 256)
+    __shared__ float s_a[RB * HID];
+    __shared__ float s_h[RB * HID];
+    __shared__ float s_xh[RB * HID];
+    __shared__ float s_rs[RB * 16];
+    __shared__ float s_o[RB * HID];
+    const int t = threadIdx.x;
+    const int row0 = blockIdx.x * RB;
+    for (int i = t; i < RB * n_in; i += kThreads) {
+        const int r = i / n_in, k = i - r * n_in;
+        s_x[r * HID + k] = row0 + r < M ? __fmul_rn(fea[(size_t)(row0 + r) * n_fea + in_idx[k]], scale) : 0.f;
+    }
+    for (int i = t; i < RB * n_fea; i += kThreads) {                       // denoised_fea = fea.clone()
+        const int r = i / n_fea, k = i - r * n_fea;
+        if (row0 + r < M) out[(size_t)(row0 + r) * n_fea + k] = fea[(size_t)(row0 + r) * n_fea + k];
+    }
+    __syncthreads();
+    dense_fwd(W.w1t, W.b1, n_in, HID, s_x, HID, s_a, HID);
+    gn_relu_fwd(W.g1, W.be1, s_a, s_h, s_xh, s_rs);
+    dense_fwd(W.w2t, W.b2, HID, HID, s_h, HID, s_a, HID);
+    gn_relu_fwd(W.g2, W.be2, s_a, s_h, s_xh, s_rs);
+    dense_fwd(W.w3t, W.b3, HID, n_out, s_h, HID, s_o, HID);
+    for (int i = t; i < RB * n_out; i += kThreads) {
+        const int r = i / n_out, k = i - r * n_out;
+        if (row0 + r < M) out[(size_t)(row0 + r) * n_fea + out_idx[k]] = __fdiv_rn(s_o[r * HID + k], scale);
+    }
+}
+
+}  // namespace
+
+// Packed blob (floats): W1^T [n_in,256], b1, gamma1, beta1 [256 each], W2^T [256,256], b2, gamma2, beta2, W3^T [256,n_out], b3 [n_out].
+SH_EXPORT size_t sh_pose_denoiser_blob_floats(int n_in, int n_out) {
+    return (size_t)n_in * HID + 3 * HID + (size_t)HID * HID + 3 * HID + (size_t)HID * n_out + n_out;
+}
+
+// fea fp32 [M,n_fea]; in_idx int32 [n_in] (<= 256), out_idx int32 [n_out] (<= 256), entries in [0,n_fea); out fp32 [M,n_fea]
+SH_EXPORT int sh_pose_denoiser_fwd(const void* fea, const void* in_idx, const void* out_idx, const void* blob, int M, int n_fea,
+                                    int n_in, int n_out, float scale, void* out, void* stream) {
+    SH_REQUIRE(M >= 0 && n_fea >= 1 && n_in >= 1 && n_in <= HID && n_out >= 1 && n_out <= HID, "sh_pose_denoiser_fwd: bad sizes");
+    if (M == 0) return SH_OK;
+    SH_REQUIRE(fea && in_idx && out_idx && blob && out, "sh_pose_denoiser_fwd: null pointer");
+    SH_REQUIRE(scale != 0.f, "sh_pose_denoiser_fwd: scale must be non-zero");
+    const float* p = (const float*)blob;
+    auto take = [&](size_t n) { const float* q = p; p += n; return q; };
+    DenWeights W;
+    W.w1t = take((size_t)n_in * HID); W.b1 = take(HID); W.g1 = take(HID); W.be1 = take(HID);
+    W.w2t = take((size_t)HID * HID); W.b2 = take(HID); W.g2 = take(HID); W.be2 = take(HID);
+    W.w3t = take((size_t)HID * n_out); W.b3 = take(n_out);
+    pose_denoiser_kernel<<<sh_div_up(M, RB), kThreads, 0, (cudaStream_t)stream>>>((const float*)fea, (const int*)in_idx, (const int*)out_idx, W, M,
+                                                                                   n_fea, n_in, n_out, scale, (float*)out);
+    SH_CHECK_LAUNCH("pose_denoiser_kernel");
+    return SH_OK;
+}

@@ -367,6 +367,18 @@ def resize_crop(depth_maps, u_scales, v_scales):
     return out
 
 
+def pose_denoiser_fwd(fea, in_idx, out_idx, blob, scale):
+    """fea [M,n_fea] fp32, in_idx / out_idx int32 -> out [M,n_fea] (sh_pose_denoiser_fwd)."""
+    M, n_fea = fea.shape
+    n_in, n_out = in_idx.numel(), out_idx.numel()
+    if blob.numel() != _lib.lib().sh_pose_denoiser_blob_floats(n_in, n_out):
+        raise RuntimeError('pose_denoiser_fwd: weight blob has the wrong size')
+    out = torch.empty_like(fea)
+    _call('sh_pose_denoiser_fwd', _chk(fea, name='fea'), _chk(in_idx, torch.int32, 'in_idx'), _chk(out_idx, torch.int32, 'out_idx'),
+          _chk(blob, name='blob'), M, n_fea, n_in, n_out, float(scale), out.data_ptr(), _stream())
+    return out
+
+
 def sample_poses(u, offsets):
     """u: fp32 uniforms (any shape, contiguous), offsets int32 [n] -> poses [n,26] (sh_sample_poses)."""
     n = offsets.numel()

@@ -247,6 +247,25 @@ def test_shard_batch_loader_prefetch():
         nd.ShardBatchLoader(ds, 9, device=DEV)
 
 
+def test_pose_denoiser_against_golden_and_oracle():
+    """PoseDenoiser eval forward as one kernel: the reference's output on the fixture (3-D and 2-D inputs), the oracle on a
+    larger random batch with a ragged row count, untouched coordinates copied bit for bit."""
+    from spherehand_b200.network import pose_denoiser as pd
+    g = golden('pose_denoiser')
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('sd.')}
+    net = pd.PoseDenoiser().to(DEV).eval()
+    net.load_state_dict(sd)
+    out3 = net(cu(g['joints']))
+    assert out3.shape == (7, 41, 3) and rel_err(out3.cpu(), g['out3']) < 1e-5
+    assert rel_err(net(cu(g['joints']).reshape(7, -1)[:3].contiguous()).cpu(), g['out2']) < 1e-5
+    keep = np.setdiff1d(np.arange(123), g['output_indices'])
+    assert np.array_equal(out3.reshape(7, -1).cpu().numpy()[:, keep], g['joints'].reshape(7, -1)[:, keep])
+    x = torch.randn(1001, 123, generator=torch.Generator().manual_seed(9)) * 50
+    want = losses.pose_denoiser_forward(sd, x, torch.from_numpy(g['input_indices']), torch.from_numpy(g['output_indices']))
+    assert rel_err(net(x.to(DEV)).cpu(), want) < 1e-5
+    assert net(torch.zeros(0, 123, device=DEV)).shape == (0, 123)
+
+
 def test_network_heads_and_full_criterion(hand_model):
     # soft-argmax head through autograd
     g = golden('softargmax')

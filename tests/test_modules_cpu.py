@@ -120,6 +120,24 @@ def test_npy_shard_reader_and_writer(tmp_path):
         nd.ShardBatchLoader(ds, 2, device='cpu')
 
 
+def test_pose_denoiser_surface():
+    from spherehand_b200.network import pose_denoiser as pd
+    g = golden('pose_denoiser')
+    net = pd.PoseDenoiser()
+    assert set(net.state_dict()) == {k[3:] for k in g if k.startswith('sd.')}          # the reference's checkpoint keys
+    assert pd.input_indices == g['input_indices'].tolist() and pd.output_indices == g['output_indices'].tolist()
+    assert net.input_fea == 112 and net.output_fea == 33 and net.scale_factor == 0.01
+    net.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('sd.')})
+    with pytest.raises(NotImplementedError):
+        net.train()(torch.zeros(2, 123))
+    with pytest.raises(RuntimeError):
+        net.eval()(torch.zeros(2, 123))                                                # CPU tensor: no fallback
+    j = torch.from_numpy(g['joints'])
+    assert abs(float(net.loss(j, torch.from_numpy(g['out3']))) - float(g['loss'])) < 1e-6 * float(g['loss'])
+    assert abs(pd.average_joint_error(j, torch.from_numpy(g['out3']), pd.key_points)
+               - float((j[:, :11] - torch.from_numpy(g['out3'])[:, :11]).norm(dim=-1).mean())) < 1e-6
+
+
 def test_no_cpu_fallback_anywhere(hand_model):
     """Every forward on CPU tensors raises (CHECK_CUDA of the reference shim, depth_rasterization_cuda.cpp:11-13): the
     product path must never silently compute on the host."""
