@@ -630,11 +630,11 @@ __global__ void __launch_bounds__(kT) stem_conv_fwd_kernel(const float* __restri
     const int cv = threadIdx.x & 7, q = threadIdx.x >> 3;            // 8 channel vectors x 32 pixel quads
     const int c0 = cv * 8;
     const int lr = q / (kStemCols / 4), lc = (q % (kStemCols / 4)) * 4;   // local output row, first local output column
-    float acc[4][8];
+    float2 acc2[4][4];                                               // [pixel][channel pair]: packed FFMA2, one issue slot per pair
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i][e] = bias[c0 + e];
+        for (int e = 0; e < 4; ++e) acc2[i][e] = make_float2(bias[c0 + 2 * e], bias[c0 + 2 * e + 1]);
 #pragma unroll
     for (int kh = 0; kh < 5; ++kh) {
         float in[11];
@@ -645,13 +645,20 @@ __global__ void __launch_bounds__(kT) stem_conv_fwd_kernel(const float* __restri
         for (int kw = 0; kw < 5; ++kw) {
             const float4 w0 = *reinterpret_cast<const float4*>(s_w + (kh * 5 + kw) * 64 + c0);
             const float4 w1 = *reinterpret_cast<const float4*>(s_w + (kh * 5 + kw) * 64 + c0 + 4);
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) {
+                const float2 iv = make_float2(in[2 * i + kw], in[2 * i + kw]);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(in[2 * i + kw], wv[e], acc[i][e]);
+                for (int e = 0; e < 4; ++e) acc2[i][e] = __ffma2_rn(iv, wv[e], acc2[i][e]);
+            }
         }
     }
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc[i][2 * e] = acc2[i][e].x; acc[i][2 * e + 1] = acc2[i][e].y; }
     const int oh = oh0 + lr;
     float st[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
