@@ -76,6 +76,7 @@ class SelfSupTrainStep:
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.projected_dms = None
         self._graphs = {}
+        self._side = torch.cuda.Stream(device=dev)             # the VAE prior runs here, under the projection loss
         self.launches_per_step = None
 
     # ------------------------------------------------------------------ host-side plumbing
@@ -140,16 +141,29 @@ class SelfSupTrainStep:
             xyz, sse = ops.softargmax_fwd(score, J, Ns, uv_t, 1.0 / self.depth_scale, want_sse=True)
             joints = xyz[Ns:].view(B, V, J, 3)
             loss_mv = g_mv = loss_p = g_p = loss_v = g_v = None
+            joined = None
+            if self.flags['prior']:
+                # The VAE prior is a latency chain of 14 small dense layers on M/4 CTAs: it goes out FIRST, on a side stream, and
+                # runs underneath the projection loss (which fills the GPU) instead of in front of it.  Inside the CUDA graph the
+                # fork / join events become graph edges.
+                main = torch.cuda.current_stream(self.dev)
+                fork = torch.cuda.Event()
+                fork.record(main)
+                self._side.wait_event(fork)
+                with torch.cuda.stream(self._side):
+                    x = torch.empty((M, J * 3), device=self.dev, dtype=torch.float32)
+                    ops.scale(xyz[Ns:], 0.01, x)
+                    loss_v, g_v = ops.vae_prior_fwdbwd(x, self.vae_eps[si], self.vae_blob, M_mean=M * self.world_size)
+                    joined = torch.cuda.Event()
+                    joined.record(self._side)
             if self.flags['proj']:
                 loss_mv, proj, g_mv = ops.mvproj_loss_fwdbwd(self.cams, self.inv_cams, joints, self.real, hand.radii, is_mv)
                 projected.append(proj)
             pf = (1 if self.flags['cons'] else 0) | (2 if self.flags['collision'] else 0) | (4 if self.flags['bone'] else 0)
             if pf:
                 loss_p, g_p = ops.pose_losses_fwdbwd(self.cams, joints, flags=pf)
-            if self.flags['prior']:
-                x = torch.empty((M, J * 3), device=self.dev, dtype=torch.float32)
-                ops.scale(xyz[Ns:], 0.01, x)
-                loss_v, g_v = ops.vae_prior_fwdbwd(x, self.vae_eps[si], self.vae_blob, M_mean=M * self.world_size)
+            if joined is not None:
+                torch.cuda.current_stream(self.dev).wait_event(joined)
             gxyz = torch.empty_like(xyz)
             ops.step_combine(xyz, Ns, M, J, hw, w8, gxyz, self.terms, g_mvproj=g_mv, g_pose3=g_p, g_prior=g_v,
                              target_xyz4=xyz_t, loss_mv3=loss_mv, loss_pose3=loss_p, loss_prior3=loss_v, sse2=sse,
