@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(kT) gn_relu_fwd_kernel(const __nv_bfloat16* __
 //            stored with one bulk async copy; optional column sum of the ROUNDED dx into colsum[C].
 constexpr int kBwdMaxElems = 8192;      // slab elements (pixels x channels): 16 KB bf16 per tensor, 48 KB per block
 constexpr int kBT = 128;                // threads per block: 4 blocks (16 warps) per SM in different phases
+constexpr int kBwdSmallElems = 16384;   // a whole sample of up to this many elements is handled by one block
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -913,17 +914,23 @@ SH_EXPORT int sh_gn_relu_bwd(const void* da, const void* x, const void* stats_in
     cudaStream_t st = (cudaStream_t)stream;
     SH_REQUIRE(kBT % (C / 8) == 0, "sh_gn_relu_bwd: C / 8 must divide 128");
     const int rows = kBT / (C / 8);
-    // pixels per block: the largest slab that fits (16 KB per tensor), halved while that leaves SMs idle
+    // pixels per block: the largest slab that fits (16 KB per tensor), halved while that leaves SMs idle.  A sample of up to
+    // kBwdSmallElems elements (the 4x4 and 8x8 levels of the hourglass) stays in ONE block: 96 KB of slabs, two blocks per
+    // SM, and no cross-block publish / wait chain at all (that chain, not the data, is what a 14 us launch on 8 MB was made of).
     int ppb = kBwdMaxElems / C;
-    if (ppb > HW) ppb = HW;
-    while (ppb > 2 * rows && (long)N * ((HW + ppb - 1) / ppb) < 2L * SH_NUM_SMS) ppb = (ppb + 1) / 2;
+    if ((long)HW * C <= kBwdSmallElems) {
+        ppb = HW;
+    } else {
+        if (ppb > HW) ppb = HW;
+        while (ppb > 2 * rows && (long)N * ((HW + ppb - 1) / ppb) < 2L * SH_NUM_SMS) ppb = (ppb + 1) / 2;
+    }
     const int nblk = sh_div_up(HW, ppb);
     SH_REQUIRE(nblk <= 128, "sh_gn_relu_bwd: sample too large for the co-resident per-sample barrier (HW*C <= 2M elements)");
     SH_CUDA(cudaMemsetAsync(red, 0, sh_gn_relu_bwd_scratch_words(N, G) * 4, st));
     const size_t smem = (size_t)ppb * C * 2 * (addend ? 3 : 2);
     static bool attr = false;
     if (!attr) {
-        SH_CUDA(cudaFuncSetAttribute(gn_relu_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kBwdMaxElems * 2));
+        SH_CUDA(cudaFuncSetAttribute(gn_relu_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kBwdSmallElems * 2));
         attr = true;
     }
     dim3 grid(nblk, N);

@@ -128,7 +128,8 @@ def test_conv3x3_halo_mode(N, H, W, Cin, Cout):
     assert rel_err(y32.cpu(), y32b.cpu()) < 1e-5
 
 
-@pytest.mark.parametrize('N,H,C,G', [(3, 16, 128, 16), (2, 32, 256, 16), (2, 32, 64, 16), (2, 32, 64, 4)])
+@pytest.mark.parametrize('N,H,C,G', [(3, 16, 128, 16), (2, 32, 256, 16), (2, 32, 64, 16), (2, 32, 64, 4),
+                                     (5, 4, 256, 16), (3, 8, 256, 16), (4, 8, 128, 16)])     # the last three: one block per sample
 def test_gn_relu_fwd_bwd(N, H, C, G):
     torch.manual_seed(C + G)
     x = (torch.randn(N, C, H, H, device=DEV) * 2 + 0.5).to(BF16).float().requires_grad_(True)
