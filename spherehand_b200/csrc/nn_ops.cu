@@ -224,22 +224,10 @@ __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16
     const int gs = C / G;
     const float cnt_inv = 1.f / ((float)HW * gs);
     if (threadIdx.x == 0) {
+        // the slab loads go out before anything else: the statistics fetch and the table clearing below overlap them
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
-    }
-    if (threadIdx.x < G) {
-        const float s1 = stats_in[((size_t)n * G + threadIdx.x) * 2], s2 = stats_in[((size_t)n * G + threadIdx.x) * 2 + 1];
-        const float mean = s1 * cnt_inv;
-        const float var = fmaxf(s2 * cnt_inv - mean * mean, 0.f);
-        s_mr[threadIdx.x * 2] = mean;
-        s_mr[threadIdx.x * 2 + 1] = rsqrtf(var + eps);
-    }
-    if (threadIdx.x < 64) s_red[threadIdx.x] = 0.f;
-    for (int i = threadIdx.x; i < 512; i += kBT) (&s_gb[0][0])[i] = 0.f;
-    for (int i = threadIdx.x; i < 256; i += kBT) s_cs[i] = 0.f;
-    __syncthreads();
-    if (threadIdx.x == 0) {
         mbar_expect_tx(&s_bar[0], 2 * bytes);
         for (uint32_t o = 0; o < bytes; o += 4096) {          // 4 KB pieces: several bulk requests in flight per tensor
             const uint32_t b = min(4096u, bytes - o);
@@ -252,6 +240,17 @@ __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16
                 bulk_g2s(s_add + o, reinterpret_cast<const uint8_t*>(addend + goff) + o, min(4096u, bytes - o), &s_bar[1]);
         }
     }
+    if (threadIdx.x < G) {
+        const float s1 = stats_in[((size_t)n * G + threadIdx.x) * 2], s2 = stats_in[((size_t)n * G + threadIdx.x) * 2 + 1];
+        const float mean = s1 * cnt_inv;
+        const float var = fmaxf(s2 * cnt_inv - mean * mean, 0.f);
+        s_mr[threadIdx.x * 2] = mean;
+        s_mr[threadIdx.x * 2 + 1] = rsqrtf(var + eps);
+    }
+    if (threadIdx.x < 64) s_red[threadIdx.x] = 0.f;
+    for (int i = threadIdx.x; i < 512; i += kBT) (&s_gb[0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < 256; i += kBT) s_cs[i] = 0.f;
+    __syncthreads();
     const int vecs = C / 8, rows = kBT / vecs;
     const int cv = threadIdx.x % vecs, r0 = threadIdx.x / vecs;
     const int c0 = cv * 8;
