@@ -275,12 +275,15 @@ __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16
             const bf8 xv = load8(reinterpret_cast<const __nv_bfloat16*>(s_x + o));
             const bf8 gv = load8(reinterpret_cast<const __nv_bfloat16*>(s_da + o));
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float y = fmaf(xv.v[e], ka[e], kb[e]);
-                const float xh = fmaf(xv.v[e], rs[e], nm[e]);
-                const float dy = y > 0.f ? gv.v[e] : 0.f;
-                dg[e] = fmaf(dy, xh, dg[e]);
-                db[e] += dy;
+            for (int j = 0; j < 4; ++j) {                     // packed f32x2: one issue slot per channel pair, same IEEE results
+                const float2 x2 = make_float2(xv.v[2 * j], xv.v[2 * j + 1]);
+                const float2 y = __ffma2_rn(x2, make_float2(ka[2 * j], ka[2 * j + 1]), make_float2(kb[2 * j], kb[2 * j + 1]));
+                const float2 xh = __ffma2_rn(x2, make_float2(rs[2 * j], rs[2 * j + 1]), make_float2(nm[2 * j], nm[2 * j + 1]));
+                const float2 dy = make_float2(y.x > 0.f ? gv.v[2 * j] : 0.f, y.y > 0.f ? gv.v[2 * j + 1] : 0.f);
+                const float2 g2 = __ffma2_rn(dy, xh, make_float2(dg[2 * j], dg[2 * j + 1]));
+                const float2 b2 = __fadd2_rn(make_float2(db[2 * j], db[2 * j + 1]), dy);
+                dg[2 * j] = g2.x; dg[2 * j + 1] = g2.y;
+                db[2 * j] = b2.x; db[2 * j + 1] = b2.y;
             }
         }
         block_channel_sum<kBT>(dg, s_gb[0], vecs, c0);
@@ -335,12 +338,15 @@ __global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16
         bf8 r;
         if (addend) r = load8(reinterpret_cast<const __nv_bfloat16*>(s_add + o));
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float y = fmaf(xv.v[e], ka[e], kb[e]);
-            const float dy = y > 0.f ? gv.v[e] : 0.f;
-            float d = fmaf(dy, ka[e], fmaf(xv.v[e], k2[e], k3[e]));
-            if (addend) d += r.v[e];
-            r.v[e] = d;
+        for (int j = 0; j < 4; ++j) {
+            const float2 x2 = make_float2(xv.v[2 * j], xv.v[2 * j + 1]);
+            const float2 ka2 = make_float2(ka[2 * j], ka[2 * j + 1]);
+            const float2 y = __ffma2_rn(x2, ka2, make_float2(kb[2 * j], kb[2 * j + 1]));
+            const float2 dy = make_float2(y.x > 0.f ? gv.v[2 * j] : 0.f, y.y > 0.f ? gv.v[2 * j + 1] : 0.f);
+            float2 d = __ffma2_rn(dy, ka2, __ffma2_rn(x2, make_float2(k2[2 * j], k2[2 * j + 1]), make_float2(k3[2 * j], k3[2 * j + 1])));
+            if (addend) d = __fadd2_rn(d, make_float2(r.v[2 * j], r.v[2 * j + 1]));
+            r.v[2 * j] = d.x;
+            r.v[2 * j + 1] = d.y;
         }
         store8(reinterpret_cast<__nv_bfloat16*>(s_da + o), r);
         if (colsum) {
