@@ -126,16 +126,16 @@ __device__ __forceinline__ void row_stats(const uint32_t (&packed)[NW], bool row
     float vals[V];
 #pragma unroll
     for (int gi = 0; gi < NG; ++gi) {
-        float s1 = 0.f, s2 = 0.f;
+        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);      // packed f32x2: one issue slot per channel pair
 #pragma unroll
         for (int j = 0; j < GS / 2; ++j) {
             const uint32_t pk = packed[gi * (GS / 2) + j];
-            const float x0 = __uint_as_float(pk << 16), x1 = __uint_as_float(pk & 0xffff0000u);
-            s1 += x0 + x1;
-            s2 += x0 * x0 + x1 * x1;
+            const float2 xp = make_float2(__uint_as_float(pk << 16), __uint_as_float(pk & 0xffff0000u));
+            s1 = __fadd2_rn(s1, xp);
+            s2 = __ffma2_rn(xp, xp, s2);
         }
-        vals[2 * gi] = row_ok ? s1 : 0.f;
-        vals[2 * gi + 1] = row_ok ? s2 : 0.f;
+        vals[2 * gi] = row_ok ? s1.x + s1.y : 0.f;
+        vals[2 * gi + 1] = row_ok ? s2.x + s2.y : 0.f;
     }
     int base = 0;
     Bfly<V, R / 2>::run(vals, lane, base);
@@ -407,7 +407,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
                         const uint32_t chunk16 = (uint32_t)(hh * 4 + q);
                         float f[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + s_bias[ch0 + q * 8 + e];
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 bb = *reinterpret_cast<const float2*>(s_bias + ch0 + q * 8 + 2 * e);
+                            const float2 t2 = __fadd2_rn(make_float2(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1])), bb);
+                            f[2 * e] = t2.x;
+                            f[2 * e + 1] = t2.y;
+                        }
                         if (p.y_nchw && row_ok) {
                             const size_t hw = (size_t)g.H * g.W;
                             float* o = p.y_nchw + ((size_t)n * g.cout + ch0 + q * 8) * hw + (size_t)h * g.W + w;

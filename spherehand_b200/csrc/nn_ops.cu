@@ -47,12 +47,18 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, bf8& x) {
 // Per-thread running sum / sumsq of its 8 channels (the channel vector of a thread never changes, so its group(s)
 // are fixed): st = {s1, s2} for gs >= 8, {s1_lo, s2_lo, s1_hi, s2_hi} for gs == 4.  Flushed once into s_st[G][2].
 __device__ __forceinline__ void stats_accum(float* st, const bf8& x, int gs) {
+    // packed f32x2 partial sums over the channel pairs (short dependency chains, one issue slot per pair), folded per call
+    const float2 p0 = make_float2(x.v[0], x.v[1]), p1 = make_float2(x.v[2], x.v[3]), p2 = make_float2(x.v[4], x.v[5]),
+                 p3 = make_float2(x.v[6], x.v[7]);
+    const float2 slo = __fadd2_rn(p0, p1), shi = __fadd2_rn(p2, p3);
+    const float2 qlo = __ffma2_rn(p1, p1, __fmul2_rn(p0, p0)), qhi = __ffma2_rn(p3, p3, __fmul2_rn(p2, p2));
     if (gs >= 8) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { st[0] += x.v[e]; st[1] += x.v[e] * x.v[e]; }
+        const float2 s = __fadd2_rn(slo, shi), q = __fadd2_rn(qlo, qhi);
+        st[0] += s.x + s.y;
+        st[1] += q.x + q.y;
     } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { st[0] += x.v[e]; st[1] += x.v[e] * x.v[e]; st[2] += x.v[4 + e]; st[3] += x.v[4 + e] * x.v[4 + e]; }
+        st[0] += slo.x + slo.y; st[1] += qlo.x + qlo.y;
+        st[2] += shi.x + shi.y; st[3] += qhi.x + qhi.y;
     }
 }
 // Sum `v[8]` (this thread's 8 channels c0..c0+7) over all threads of the block that own the same channels, into
@@ -165,8 +171,10 @@ __global__ void __launch_bounds__(kT) gn_relu_fwd_kernel(const __nv_bfloat16* __
             bf8 v;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                v.v[2 * e] = fmaxf(fmaf(__uint_as_float(r[e] << 16), ka[2 * e], kb[2 * e]), 0.f);
-                v.v[2 * e + 1] = fmaxf(fmaf(__uint_as_float(r[e] & 0xffff0000u), ka[2 * e + 1], kb[2 * e + 1]), 0.f);
+                const float2 y = __ffma2_rn(make_float2(__uint_as_float(r[e] << 16), __uint_as_float(r[e] & 0xffff0000u)),
+                                            make_float2(ka[2 * e], ka[2 * e + 1]), make_float2(kb[2 * e], kb[2 * e + 1]));
+                v.v[2 * e] = fmaxf(y.x, 0.f);
+                v.v[2 * e + 1] = fmaxf(y.y, 0.f);
             }
             store8(yb + (size_t)pp * C, v);
             if (stats_out) stats_accum(st, v, C / G_out);
