@@ -155,6 +155,10 @@ size_t sh_gn_relu_bwd_scratch_words(int N, int G);
 int sh_gn_relu_bwd(const void* da, const void* x, const void* stats_in, const void* gamma, const void* beta,
                    const void* addend, int N, int HW, int C, int G, float eps, void* red, void* dgamma, void* dbeta,
                    void* dx, void* colsum, void* stream);
+/* Same as sh_gn_relu_bwd for a `red` scratch the caller has already zeroed (one arena cleared once per backward pass). */
+int sh_gn_relu_bwd_prezeroed(const void* da, const void* x, const void* stats_in, const void* gamma, const void* beta,
+                   const void* addend, int N, int HW, int C, int G, float eps, void* red, void* dgamma, void* dbeta,
+                   void* dx, void* colsum, void* stream);
 int sh_maxpool_fwd(const void* x, int N, int H, int W, int C, void* y, void* stats_out, int G_out, void* stream);
 int sh_maxpool_bwd(const void* dy, const void* x, const void* addend, int N, int H, int W, int C, void* dx,
                    void* colsum, void* stream);

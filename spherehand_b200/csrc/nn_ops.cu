@@ -917,9 +917,9 @@ SH_EXPORT int sh_gn_relu_fwd(const void* x, const void* stats_in, const void* ga
 SH_EXPORT size_t sh_gn_relu_bwd_scratch_words(int N, int G) { return (size_t)N * G * 2 + (size_t)N; }
 
 // red: scratch of sh_gn_relu_bwd_scratch_words(N,G) words (zeroed here); dgamma/dbeta accumulated (caller zeroes once per step)
-SH_EXPORT int sh_gn_relu_bwd(const void* da, const void* x, const void* stats_in, const void* gamma, const void* beta,
-                              const void* addend, int N, int HW, int C, int G, float eps, void* red, void* dgamma, void* dbeta,
-                              void* dx, void* colsum, void* stream) {
+static int gn_relu_bwd_impl(const void* da, const void* x, const void* stats_in, const void* gamma, const void* beta,
+                            const void* addend, int N, int HW, int C, int G, float eps, void* red, void* dgamma, void* dbeta,
+                            void* dx, void* colsum, void* stream, bool zero_red) {
     SH_REQUIRE(da && x && stats_in && gamma && beta && red && dgamma && dbeta && dx, "sh_gn_relu_bwd: null pointer");
     NHWC_CHECK("sh_gn_relu_bwd");
     SH_REQUIRE(G >= 1 && G <= 32 && C % G == 0 && (C / G) % 4 == 0, "sh_gn_relu_bwd: bad grouping");
@@ -939,7 +939,7 @@ SH_EXPORT int sh_gn_relu_bwd(const void* da, const void* x, const void* stats_in
     }
     const int nblk = sh_div_up(HW, ppb);
     SH_REQUIRE(nblk <= 128, "sh_gn_relu_bwd: sample too large for the co-resident per-sample barrier (HW*C <= 2M elements)");
-    SH_CUDA(cudaMemsetAsync(red, 0, sh_gn_relu_bwd_scratch_words(N, G) * 4, st));
+    if (zero_red) SH_CUDA(cudaMemsetAsync(red, 0, sh_gn_relu_bwd_scratch_words(N, G) * 4, st));
     const size_t smem = (size_t)ppb * C * 2 * (addend ? 3 : 2);
     static bool attr = false;
     if (!attr) {
@@ -953,6 +953,18 @@ SH_EXPORT int sh_gn_relu_bwd(const void* da, const void* x, const void* stats_in
                                                (__nv_bfloat16*)dx, (float*)colsum);
     SH_CHECK_LAUNCH("gn_relu_bwd_kernel");
     return SH_OK;
+}
+
+SH_EXPORT int sh_gn_relu_bwd(const void* da, const void* x, const void* stats_in, const void* gamma, const void* beta,
+                              const void* addend, int N, int HW, int C, int G, float eps, void* red, void* dgamma, void* dbeta,
+                              void* dx, void* colsum, void* stream) {
+    return gn_relu_bwd_impl(da, x, stats_in, gamma, beta, addend, N, HW, C, G, eps, red, dgamma, dbeta, dx, colsum, stream, true);
+}
+// Same, for a `red` the caller has already cleared (e.g. one arena for all layers of a backward pass, zeroed once)
+SH_EXPORT int sh_gn_relu_bwd_prezeroed(const void* da, const void* x, const void* stats_in, const void* gamma, const void* beta,
+                                        const void* addend, int N, int HW, int C, int G, float eps, void* red, void* dgamma,
+                                        void* dbeta, void* dx, void* colsum, void* stream) {
+    return gn_relu_bwd_impl(da, x, stats_in, gamma, beta, addend, N, HW, C, G, eps, red, dgamma, dbeta, dx, colsum, stream, false);
 }
 
 SH_EXPORT int sh_maxpool_fwd(const void* x, int N, int H, int W, int C, void* y, void* stats_out, int G_out, void* stream) {

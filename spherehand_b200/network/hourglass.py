@@ -221,6 +221,7 @@ class _Run:
 
     def __init__(self, net, N, device):
         self.net, self.N, self.dev = net, N, device
+        self._gn_words = 0                 # scratch words the GroupNorm backward kernels of this pass need
         self.tape = []
         self.stats_pool = torch.zeros((160, N, 16, 2), device=device, dtype=torch.float32)
         self.stats_used = 0
@@ -291,11 +292,17 @@ class _Run:
         ops.gn_relu_fwd(x.buf, x.stats, gn.weight.data, gn.bias.data, N, x.H * x.W, x.C, G, a, st, G_out)
         net = self.net
 
+        # scratch of this layer's backward: a slice of ONE arena zeroed once per backward pass (one fill instead of a memset
+        # node per GroupNorm layer in the captured graph)
+        words = (ops.gn_relu_bwd_scratch_words(N, G) + 3) // 4 * 4
+        slot = self._gn_words
+        self._gn_words += words
+
         def bwd(da, addend=None, colsum=None):
-            red = ops.gn_relu_bwd_scratch(N, G, self.dev)
+            red = self._gn_arena[slot:slot + words]
             dx = torch.empty_like(x.buf)
             ops.gn_relu_bwd(da, x.buf, x.stats, gn.weight.data, gn.bias.data, N, x.H * x.W, x.C, G, red,
-                            net.grad_view(gn.weight), net.grad_view(gn.bias), dx, addend, colsum)
+                            net.grad_view(gn.weight), net.grad_view(gn.bias), dx, addend, colsum, prezeroed=True)
             return dx
         return a, st, bwd
 
@@ -469,6 +476,7 @@ class _Run:
     def backward(self, grad_scores):
         if hasattr(self, '_t128'):
             self._t128.zero_()
+        self._gn_arena = torch.zeros(max(self._gn_words, 1), device=self.dev, dtype=torch.float32)
         self._backward(grad_scores)
 
 

@@ -231,15 +231,21 @@ def gn_relu_fwd(x, stats_in, gamma, beta, N, HW, C, G, y, stats_out=None, G_out=
           N, HW, C, G, eps, _chk(y, BF16, 'y'), _opt(stats_out, name='stats_out'), G_out, _stream())
 
 
+def gn_relu_bwd_scratch_words(N, G):
+    return _lib.lib().sh_gn_relu_bwd_scratch_words(N, G)
+
+
 def gn_relu_bwd_scratch(N, G, device):
     """Scratch tensor sh_gn_relu_bwd needs (per-(n,g) partial sums + per-sample arrive counters)."""
     return torch.empty(_lib.lib().sh_gn_relu_bwd_scratch_words(N, G), device=device, dtype=torch.float32)
 
 
-def gn_relu_bwd(da, x, stats_in, gamma, beta, N, HW, C, G, red, dgamma, dbeta, dx, addend=None, colsum=None, eps=1e-5):
+def gn_relu_bwd(da, x, stats_in, gamma, beta, N, HW, C, G, red, dgamma, dbeta, dx, addend=None, colsum=None, eps=1e-5,
+                prezeroed=False):
+    """prezeroed: `red` is already all zero (a slice of an arena the caller cleared once): the entry skips its own memset."""
     if red.numel() < _lib.lib().sh_gn_relu_bwd_scratch_words(N, G):
         raise RuntimeError('gn_relu_bwd: scratch too small (use ops.gn_relu_bwd_scratch)')
-    _call('sh_gn_relu_bwd', _chk(da, BF16, 'da'), _chk(x, BF16, 'x'), _chk(stats_in, name='stats'), _chk(gamma, name='gamma'),
+    _call('sh_gn_relu_bwd_prezeroed' if prezeroed else 'sh_gn_relu_bwd', _chk(da, BF16, 'da'), _chk(x, BF16, 'x'), _chk(stats_in, name='stats'), _chk(gamma, name='gamma'),
           _chk(beta, name='beta'), _opt(addend, BF16, 'addend'), N, HW, C, G, eps, _chk(red, name='red'),
           _chk(dgamma, name='dgamma'), _chk(dbeta, name='dbeta'), _chk(dx, BF16, 'dx'), _opt(colsum, name='colsum'), _stream())
 
