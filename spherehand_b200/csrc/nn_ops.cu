@@ -475,21 +475,45 @@ __global__ void __launch_bounds__(kT) upsample_add_fwd_kernel(const __nv_bfloat1
     const int c0 = w.cv * 8;
     float st[4] = {0.f, 0.f, 0.f, 0.f};
     const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
-    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
-        const int yy = pp / W, xx = pp % W;
-        int y0, y1, x0, x1;
-        float wy0, wy1, wx0, wx1;
-        up_taps(yy, h, y0, y1, wy0, wy1);
-        up_taps(xx, w_, x0, x1, wx0, wx1);
-        const __nv_bfloat16* lb = low + (size_t)n * h * w_ * C + c0;
-        const bf8 a = load8(lb + ((size_t)y0 * w_ + x0) * C), b = load8(lb + ((size_t)y0 * w_ + x1) * C);
-        const bf8 c = load8(lb + ((size_t)y1 * w_ + x0) * C), d = load8(lb + ((size_t)y1 * w_ + x1) * C);
-        bf8 r = load8(up1 + ((size_t)n * HW + pp) * C + c0);
+    const __nv_bfloat16* lb = low + (size_t)n * h * w_ * C + c0;
+    constexpr int kU = 2;                        // output pixels in flight per thread (10 independent 16-byte loads)
+    for (int p0 = blockIdx.x * ppb + w.r; p0 < p_end; p0 += w.rows * kU) {
+        uint4 ra[kU], rb[kU], rc[kU], rd[kU], ru[kU];
+        float wy0[kU], wy1[kU], wx0[kU], wx1[kU];
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-            r.v[e] += wy0 * (wx0 * a.v[e] + wx1 * b.v[e]) + wy1 * (wx0 * c.v[e] + wx1 * d.v[e]);
-        store8(y + ((size_t)n * HW + pp) * C + c0, r);
-        if (stats_out) stats_accum(st, r, C / G_out);
+        for (int u = 0; u < kU; ++u) {
+            const int pp = min(p0 + u * w.rows, p_end - 1);            // clamped: the duplicate is not stored
+            const int yy = pp / W, xx = pp % W;
+            int y0, y1, x0, x1;
+            up_taps(yy, h, y0, y1, wy0[u], wy1[u]);
+            up_taps(xx, w_, x0, x1, wx0[u], wx1[u]);
+            ra[u] = *reinterpret_cast<const uint4*>(lb + ((size_t)y0 * w_ + x0) * C);
+            rb[u] = *reinterpret_cast<const uint4*>(lb + ((size_t)y0 * w_ + x1) * C);
+            rc[u] = *reinterpret_cast<const uint4*>(lb + ((size_t)y1 * w_ + x0) * C);
+            rd[u] = *reinterpret_cast<const uint4*>(lb + ((size_t)y1 * w_ + x1) * C);
+            ru[u] = *reinterpret_cast<const uint4*>(up1 + ((size_t)n * HW + pp) * C + c0);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int pp = p0 + u * w.rows;
+            if (pp >= p_end) break;
+            const uint32_t wa[4] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w}, wb[4] = {rb[u].x, rb[u].y, rb[u].z, rb[u].w};
+            const uint32_t wc[4] = {rc[u].x, rc[u].y, rc[u].z, rc[u].w}, wd[4] = {rd[u].x, rd[u].y, rd[u].z, rd[u].w};
+            const uint32_t wu[4] = {ru[u].x, ru[u].y, ru[u].z, ru[u].w};
+            bf8 r;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a0 = __uint_as_float(wa[e] << 16), a1 = __uint_as_float(wa[e] & 0xffff0000u);
+                const float b0 = __uint_as_float(wb[e] << 16), b1 = __uint_as_float(wb[e] & 0xffff0000u);
+                const float c0f = __uint_as_float(wc[e] << 16), c1f = __uint_as_float(wc[e] & 0xffff0000u);
+                const float d0 = __uint_as_float(wd[e] << 16), d1 = __uint_as_float(wd[e] & 0xffff0000u);
+                // same expression as before: up1 + wy0*(wx0*a + wx1*b) + wy1*(wx0*c + wx1*d)
+                r.v[2 * e] = __uint_as_float(wu[e] << 16) + (wy0[u] * (wx0[u] * a0 + wx1[u] * b0) + wy1[u] * (wx0[u] * c0f + wx1[u] * d0));
+                r.v[2 * e + 1] = __uint_as_float(wu[e] & 0xffff0000u) + (wy0[u] * (wx0[u] * a1 + wx1[u] * b1) + wy1[u] * (wx0[u] * c1f + wx1[u] * d1));
+            }
+            store8(y + ((size_t)n * HW + pp) * C + c0, r);
+            if (stats_out) stats_accum(st, r, C / G_out);
+        }
     }
     if (stats_out) stats_flush_block<kT>(st, s_st, w.vecs, c0, C / G_out, G_out, stats_out + (size_t)n * G_out * 2);
 }
