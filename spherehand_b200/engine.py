@@ -76,6 +76,7 @@ class SelfSupTrainStep:
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.projected_dms = None
         self._graphs = {}
+        self._staging = None                                   # prefetch_batch / commit_batch
         self._side = torch.cuda.Stream(device=dev)             # the VAE prior runs here, under the projection loss
         self.launches_per_step = None
 
@@ -91,6 +92,34 @@ class SelfSupTrainStep:
         self.inv_cams.copy_(inv_camera_poses, non_blocking=non_blocking)
         self.poses.copy_(pose_parameters, non_blocking=non_blocking)
         return real_dms.numel() * 4 + 2 * camera_poses.numel() * 4 + pose_parameters.numel() * 4
+
+    def prefetch_batch(self, real_dms, camera_poses, inv_camera_poses, pose_parameters):
+        """Start the host->device copies of the NEXT batch (pinned host tensors) on a copy stream into staging buffers; they run
+        underneath the current step.  `commit_batch()` then moves them into the static buffers the captured graph reads
+        (device-to-device, microseconds).  Returns the bytes that cross the host link."""
+        if self._staging is None:
+            self._staging = [torch.empty_like(t) for t in (self.real, self.cams, self.inv_cams, self.poses)]
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._staged, self._committed = torch.cuda.Event(), torch.cuda.Event()
+            self._committed.record(torch.cuda.current_stream(self.dev))
+        self._copy_stream.wait_event(self._committed)          # the previous commit has finished reading the staging buffers
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._staging, (real_dms, camera_poses, inv_camera_poses, pose_parameters)):
+                dst.copy_(src, non_blocking=True)
+            self._staged.record(self._copy_stream)
+        self._has_staged = True
+        return sum(t.numel() * 4 for t in self._staging)
+
+    def commit_batch(self):
+        """Make the prefetched batch the current one (see prefetch_batch)."""
+        if not getattr(self, '_has_staged', False):
+            raise RuntimeError('commit_batch: no batch has been prefetched')
+        main = torch.cuda.current_stream(self.dev)
+        main.wait_event(self._staged)
+        for dst, src in zip((self.real, self.cams, self.inv_cams, self.poses), self._staging):
+            dst.copy_(src, non_blocking=True)
+        self._committed.record(main)
+        self._has_staged = False
 
     def sample_poses(self, generator=None, sequential=True):
         """Fill the synthetic-branch poses on the device with the batched JointAngleDataset sampler (dataset/joint_angle.py of the

@@ -173,3 +173,26 @@ def test_checkpoint_roundtrip_in_the_reference_format(hand_model, tmp_path):
     tb = b.step(is_mv=True).clone()
     ta = a.step(is_mv=True).clone()
     assert same_terms(ta, tb)
+
+
+def test_prefetch_commit_equals_load_batch(hand_model):
+    """The double-buffered input path (prefetch_batch on a copy stream + commit_batch) delivers the same buffers as load_batch,
+    batch after batch, also when the next prefetch is issued before the current step has run."""
+    B, V, Ns, S, stacks = 2, 3, 2, 64, 1
+    step, _, _, batch = make_step(hand_model, B, V, Ns, S, stacks, use_graph=False)
+    with pytest.raises(RuntimeError):
+        step.commit_batch()
+    gen = torch.Generator().manual_seed(9)
+    batches = []
+    for _ in range(3):
+        batches.append([(t + torch.rand(t.shape, generator=gen) * 0.01).pin_memory() for t in (batch['real'], batch['cams'], batch['inv_cams'], batch['poses'])])
+    n = step.prefetch_batch(*batches[0])
+    assert n == sum(t.numel() * 4 for t in batches[0])
+    for k in range(3):
+        step.commit_batch()
+        if k + 1 < 3:
+            step.prefetch_batch(*batches[k + 1])           # overlaps the step below
+        step.draw_randoms()
+        step.step(is_mv=True)
+        for buf, want in zip((step.real, step.cams, step.inv_cams, step.poses), batches[k]):
+            assert torch.equal(buf.cpu(), want)
