@@ -164,3 +164,26 @@ def hourglass_forward(x, sd, num_stacks=1, prefix='', round_bf16=False):
             t = q(x + F.conv2d(y, q(sd['%sfc_.%d.weight' % (p, i)]), sd['%sfc_.%d.bias' % (p, i)]))
             x = q(t + F.conv2d(q(score), q(sd['%sscore_.%d.weight' % (p, i)]), sd['%sscore_.%d.bias' % (p, i)]))
     return outs, latents
+
+
+def two_stack_from_trained(sd1, seed=11, gain=0.05):
+    """A 2-stack state_dict built from the reference's trained 1-stack weights (pretrained/synthetic.pth): the trunk and stack 0
+    are the trained tensors, stack 1 (`hg.1`, `res.1`, `fc.1`, `score.1`) is a copy of stack 0 and the two inter-stack
+    re-injection convolutions (`fc_.0`, `score_.0`, hourglass.py:169-172 — absent from a 1-stack checkpoint) are small
+    deterministic weights (unit-gain U(-1,1) * `gain`, zero bias), so both stacks produce the peaked heat-maps of a trained
+    network.  A recipe, not an asset: fixtures at BASELINE.json's 2-stack shape are generated from and tested with it."""
+    sd = {}
+    for i, (name, shp) in enumerate(param_shapes(82, 2).items()):
+        src = name
+        for mod in ('hg.1.', 'res.1.', 'fc.1.', 'score.1.'):
+            if name.startswith(mod):
+                src = mod[:-2] + '0.' + name[len(mod):]
+        if src in sd1:
+            sd[name] = torch.as_tensor(sd1[src]).clone().float()
+        elif len(shp) == 4:
+            fan_in = shp[1] * shp[2] * shp[3]
+            u = det_uniform(int(np.prod(shp)), seed * 1000 + i).reshape(shp) * np.float32(gain * np.sqrt(3.0 / fan_in))
+            sd[name] = torch.from_numpy(np.ascontiguousarray(u.astype(np.float32)))
+        else:
+            sd[name] = torch.zeros(shp)
+    return sd
