@@ -67,6 +67,36 @@ def build(force=False):
     return target
 
 
+REF_TREE = os.path.join(OUT, "reference")
+_ASSETS = ("mesh/model/preprocessed_hand.pkl", "mesh/model/pose_prior.pkl", "mesh/model/pose_vae.pth",
+           "mesh/model/pose_denoiser.pth", "pretrained/synthetic.pth")
+
+
+def stage_reference(force=False):
+    """Copy the reference's Python modules of the path and the assets they open at import time (network/constants.py:4-8,
+    network/pose_vae.py:20, engine.py:72) into oracle/_ref/reference/ (git-ignored, NOT gpurun-ignored: it travels to the GPU
+    box like the compiled kernel).  Byte-for-byte copies, nothing edited; only bench.py's reference-GPU leg (oracle/ref_gpu.py)
+    and the drop-in tests read them.  A no-op on the GPU box."""
+    if not os.path.isdir(os.path.join(REF, "network")):
+        return REF_TREE if os.path.isdir(REF_TREE) else None
+    stamp = os.path.join(REF_TREE, ".staged")
+    if os.path.exists(stamp) and not force:
+        return REF_TREE
+    for pkg in ("mesh", "network", "dataset"):
+        dst = os.path.join(REF_TREE, pkg)
+        os.makedirs(dst, exist_ok=True)
+        for fn in sorted(os.listdir(os.path.join(REF, pkg))):
+            if fn.endswith(".py"):
+                shutil.copyfile(os.path.join(REF, pkg, fn), os.path.join(dst, fn))
+    os.makedirs(os.path.join(REF_TREE, "mesh", "cuda_kernel"), exist_ok=True)
+    shutil.copyfile(os.path.join(SRC, "__init__.py"), os.path.join(REF_TREE, "mesh", "cuda_kernel", "__init__.py"))
+    for a in _ASSETS:
+        os.makedirs(os.path.dirname(os.path.join(REF_TREE, a)), exist_ok=True)
+        shutil.copyfile(os.path.join(REF, a), os.path.join(REF_TREE, a))
+    open(stamp, "w").write("staged from %s\n" % REF)
+    return REF_TREE
+
+
 def load():
     """Import the pre-built module (needs a CUDA device to be useful)."""
     import importlib.util
@@ -83,3 +113,4 @@ def load():
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(stage_reference(force="--force" in sys.argv))

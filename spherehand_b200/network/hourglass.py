@@ -188,11 +188,15 @@ class HourglassNet(nn.Module):
         self._last_run = ctx
         return scores, latents
 
-    def run_backward(self, grad_scores):
-        """grad_scores: list of fp32 [N,num_outputs,h,w] (or None) -> gradients accumulated into the flat grad buffer."""
+    def run_backward(self, grad_scores, run=None):
+        """grad_scores: list of fp32 [N,num_outputs,h,w] (or None) -> gradients accumulated into the flat grad buffer.
+        run: the tape of the forward pass to differentiate (default: the most recent run_forward)."""
+        run = run if run is not None else self._last_run
+        if run is None:
+            raise RuntimeError('run_backward: no recorded forward pass (the last forward ran with gradients disabled)')
         self._flat_grad.zero_()
         self._wg3_scratch.zero_()
-        self._last_run.backward(grad_scores)
+        run.backward(grad_scores)
         if self._wg3_table.shape[0]:
             ops.unpack_wgrad_batch(self._wg3_table, self._wg3_scratch, self._flat_grad)
         return self._flat_grad
@@ -203,6 +207,10 @@ class _HourglassFn(torch.autograd.Function):
     def forward(ctx, net, x, *params):
         scores, latents = net.run_forward(x)
         ctx.net = net
+        # the tape of THIS forward: a later forward (an eval pass, the second branch of a two-forward step, gradient
+        # accumulation) must not be the one this node back-propagates through
+        ctx.run = net._last_run
+        net._last_run = None                 # the autograd node owns the tape; nothing is pinned once the graph is freed
         ctx.n_scores = len(scores)
         ctx.mark_non_differentiable(*latents)
         return (*scores, *latents)
@@ -211,7 +219,10 @@ class _HourglassFn(torch.autograd.Function):
     def backward(ctx, *grads):
         net = ctx.net
         gs = [g.contiguous() if g is not None else None for g in grads[:ctx.n_scores]]
-        net.run_backward(gs)
+        if ctx.run is None:
+            raise RuntimeError('HourglassNet: backward through the same forward pass twice (activations are freed after the first)')
+        net.run_backward(gs, run=ctx.run)
+        ctx.run = None
         out = [net.grad_view(p).clone() for p in net.parameters()]
         return (None, None, *out)
 

@@ -29,6 +29,18 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def elem_err(a, b, floor=1e-2):
+    """Per-element relative error with an absolute floor: max_i |a_i - b_i| / (|b_i| + floor * max|b|).  Unlike rel_err (a
+    max-normalised error) a small component may not be arbitrarily wrong: it is held to `tol * (its own size + floor * max)`,
+    i.e. with tol = 1e-4 and the default floor an absolute error of 1e-6 of the largest component (sums of fp32 terms with
+    cancellation cannot be asked for more)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if b.size == 0:
+        return 0.0
+    return float((np.abs(a - b) / (np.abs(b) + floor * max(np.abs(b).max(), 1e-30))).max())
+
+
 def mesh_dict(a):
     """The reference's `mesh` dict (mesh/preprocess.py output: vertices, faces, bones[{offset_matrix, weight_vertexid,
     weight_coeff, keypoint}]) rebuilt from the arrays of tests/golden/hand_model.npz."""

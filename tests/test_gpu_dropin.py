@@ -1,0 +1,117 @@
+"""The drop-in claim, tested: the reference's UNMODIFIED caller code runs on top of `spherehand_b200.install()`.
+
+Two import worlds, each in its own subprocess (oracle/ref_gpu.py), fed the same seeds:
+  stock   — the unmodified reference (staged by oracle/build_ref.py into oracle/_ref/reference/, never committed) in eager
+            PyTorch fp32 with its own CUDA rasteriser;
+  dropin  — `spherehand_b200.install(reference_root=...)`: mirrored modules -> the B200 kernels, everything else
+            (network/engine.py, constants.py, util_vis.py, utils_metric.py ...) -> the reference's own files.
+Checked: (1) the reference's `network.engine` imports on top of install() (CPU, no GPU needed); (2) the body of
+Engine._epoch_with_both (engine.py:349-376) gives the same loss terms and joints in both worlds on the reference's trained
+weights (bf16 tolerance: 5e-2 on the smooth terms, joints within 1e-2 of the coordinate range); (3) the reference's own
+`Engine` object — its constructor, DataLoaders, RunningAverage, visualisation dump, log file, save_model — runs one epoch
+unmodified in both worlds and logs the same averaged terms.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_TREE = os.path.join(ROOT, 'oracle', '_ref', 'reference')
+HARNESS = os.path.join(ROOT, 'oracle', 'ref_gpu.py')
+
+needs_ref = pytest.mark.skipif(not os.path.isdir(os.path.join(REF_TREE, 'network')),
+                               reason='oracle/_ref/reference not staged (python oracle/build_ref.py in the build container)')
+
+
+def run(*args, timeout=900):
+    p = subprocess.run([sys.executable, HARNESS, *args], capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    lines = [l for l in p.stdout.splitlines() if l.startswith('{')]
+    assert p.returncode == 0 and lines, 'harness failed:\n' + p.stdout[-3000:] + '\n' + p.stderr[-3000:]
+    return json.loads(lines[-1])
+
+
+@needs_ref
+def test_install_then_import_reference_engine():
+    """`install(); from network.engine import Engine` must resolve — engine.py from the checkout, the mirrored
+    modules from this package, off-path symbols (DepthResample, FuseMvPose) from the reference's own definitions."""
+    code = '''
+import sys, types
+import numpy as np
+np.float = float
+for n in ("matplotlib", "matplotlib.pyplot"):
+    sys.modules[n] = types.ModuleType(n)
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+import os
+os.chdir(%r)
+sys.path.insert(0, %r)
+import spherehand_b200
+spherehand_b200.install(reference_root=%r)
+from network.engine import Engine, Mode
+import network.engine, network.util_modules as um, mesh.multiview_utility as mu, network.hourglass as hg, mesh.render as mr
+import depth_rasterization
+assert network.engine.__file__.startswith(%r), network.engine.__file__
+assert um.HandSynthesizer.__module__ == "spherehand_b200.network.util_modules"
+assert hg.create_hourglass_network.__module__ == "spherehand_b200.network.hourglass" and mr.BallRender.__module__ == "spherehand_b200.mesh.render"
+assert um.DepthResample.__module__.startswith("_spherehand_reference.") and mu.FuseMvPose.__module__.startswith("_spherehand_reference.")
+assert depth_rasterization.forward is spherehand_b200.depth_rasterization.forward
+try:
+    um.NoSuchThing
+except AttributeError:
+    pass
+else:
+    raise SystemExit("missing symbol did not raise")
+print("ok")
+''' % (REF_TREE, ROOT, REF_TREE, REF_TREE)
+    p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and p.stdout.strip().endswith('ok'), p.stdout + p.stderr
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_dropin_step_matches_stock_reference(tmp_path):
+    out = {}
+    for mode in ('stock', 'dropin'):
+        dump = str(tmp_path / (mode + '.npz'))
+        out[mode] = run('--mode', mode, '--S', '64', '--stacks', '1', '--B', '4', '--Ns', '4', '--steps', '2', '--warmup', '1',
+                        '--weights', 'trained', '--seed', '3', '--dump', dump)
+        out[mode]['dump'] = dict(np.load(dump))
+    s, d = out['stock'], out['dropin']
+    print('stock  terms', s['terms'])
+    print('dropin terms', d['terms'])
+    js, jd = s['dump']['real_xyz0'], d['dump']['real_xyz0']
+    rng = float(js.max() - js.min())
+    dev = np.abs(js - jd)
+    print('joints: max dev %.3f mm, mean %.4f mm, range %.1f mm' % (dev.max(), dev.mean(), rng))
+    assert dev.max() <= 1e-2 * rng and dev.mean() <= 2e-3 * rng
+    total = abs(s['terms']['loss'])
+    for k, v in s['terms'].items():
+        hinge = k in ('term.collision', 'term.bone_length')
+        # hinge terms: sums of relu over a few active pairs, a 0.1 mm joint move shifts them by several %
+        tol = (0.25 * abs(v) + 2e-3 * total) if hinge else (5e-2 * abs(v) + 1e-6)
+        assert abs(d['terms'][k] - v) <= tol, (k, d['terms'][k], v)
+    bs, bd = s['dump']['ball_dms0'], d['dump']['ball_dms0']
+    both = (bs < 99) & (bd < 99)
+    assert bs.shape == bd.shape and both.sum() >= 0.97 * (bs < 99).sum() and np.abs(bs - bd)[both].mean() < 0.5
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_unmodified_engine_epoch_in_both_worlds():
+    out = {m: run('--mode', m, '--engine', '1', '--B', '8', '--seed', '5') for m in ('stock', 'dropin')}
+    s, d = out['stock'], out['dropin']
+    print('stock  engine:', s['log_line'])
+    print('dropin engine:', d['log_line'])
+    assert s['engine_file'] == d['engine_file'] and s['engine_file'].startswith(REF_TREE)          # the same unmodified caller
+    assert s['network_module'] == 'network.hourglass' and d['network_module'] == 'spherehand_b200.network.hourglass'
+    assert d['criterion_module'] == 'spherehand_b200.mesh.multiview_utility' and d['synthesizer_module'] == 'spherehand_b200.network.util_modules'
+    assert s['checkpoint_keys'] == d['checkpoint_keys'] == 148 and len(d['images_written']) == len(s['images_written']) == 1
+    total = sum(abs(v) for v in s['terms'].values())
+    for k, v in s['terms'].items():
+        hinge = k in ('collision', 'bone_length')
+        tol = (0.25 * abs(v) + 2e-3 * total) if hinge else (5e-2 * abs(v) + 2e-4)      # the log prints 4 decimals
+        assert abs(d['terms'][k] - v) <= tol, (k, d['terms'][k], v)
+    assert abs(d['avg_joint_error'] - s['avg_joint_error']) <= 0.02 * s['avg_joint_error'] + 0.5

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden, rel_err
+from conftest import golden, rel_err, elem_err
 
 pytestmark = pytest.mark.gpu
 
@@ -43,6 +43,7 @@ def test_sphere_render_golden(name):
         assert rel_err(gs[..., 3], g['grad_radii']) < 1e-4
     gc, gr = sphere.sphere_render_backward(g['grad_depth'], oi, c, r, S, S)
     assert rel_err(gs[..., :3], gc) < 1e-4 and rel_err(gs[..., 3], gr) < 1e-4
+    assert elem_err(gs[..., :3], gc) < 1e-4 and elem_err(gs[..., 3], gr) < 1e-4          # element by element
 
 
 @pytest.mark.parametrize('N,J,H,W', [(1, 1, 16, 16), (3, 41, 22, 30), (2, 64, 64, 64), (5, 48, 128, 128), (2, 7, 8, 4)])
@@ -60,6 +61,7 @@ def test_sphere_render_shapes(N, J, H, W):
     gs = ops.sphere_render_bwd(cu(gd), idx, sph).cpu().numpy()
     gc, gr = sphere.sphere_render_backward(gd, oi, c, r, W, H)
     assert rel_err(gs[..., :3], gc) < 1e-4 and rel_err(gs[..., 3], gr) < 1e-4
+    assert elem_err(gs[..., :3], gc) < 1e-4 and elem_err(gs[..., 3], gr) < 1e-4
 
 
 def test_sphere_render_edge_cases():
@@ -77,6 +79,28 @@ def test_sphere_render_edge_cases():
         ops.sphere_render_fwd(torch.zeros((1, 65, 4), device=DEV), 16, 16)
     with pytest.raises(Exception):
         ops.sphere_render_fwd(torch.zeros((1, 4, 4)), 16, 16)
+
+
+def test_sphere_render_config2_vs_oracle():
+    """BASELINE config 2 at its real size (N=256 images, J=48, 128x128, seed 1234: SURVEY §8d) against the numpy oracle: depth
+    bit for bit, arg-min index equal off exact ties, gradients (centres and radii) element by element."""
+    rng = np.random.default_rng(1234)
+    N, J, S = 256, 48, 128
+    c = np.concatenate([rng.uniform(-90, 90, (N, J, 2)), rng.uniform(-60, 60, (N, J, 1))], -1).astype(np.float32)
+    r41 = golden('hand_model')['keypoint_radius'].astype(np.float32)
+    r = np.concatenate([r41, np.full(7, 20.0, np.float32)])
+    sph = ops.pack_spheres(cu(c), cu(r))
+    depth, idx = ops.sphere_render_fwd(sph, S, S)
+    od, oi = sphere.sphere_render(c, r, S, S)
+    assert np.array_equal(depth.cpu().numpy(), od)
+    ties = sphere.sphere_render_tie_mask(c, r, S, S)
+    assert ties.mean() < 1e-3 and np.array_equal(idx.cpu().numpy()[~ties], oi[~ties])
+    gd = (rng.standard_normal((N, S, S)) * (od < 100)).astype(np.float32)
+    gs = ops.sphere_render_bwd(cu(gd), cu(oi, torch.uint8), sph).cpu().numpy()
+    gc, gr = sphere.sphere_render_backward(gd, oi, c, r, S, S)
+    e = (elem_err(gs[..., :3], gc), elem_err(gs[..., 3], gr))
+    print('config-2 renderer gradients, per-element error (floor 1e-2 of max):', e)
+    assert max(e) < 1e-4
 
 
 def test_sphere_render_full_size_properties():
@@ -117,6 +141,7 @@ def test_mvproj_loss_golden(S):
         loss3, proj, grad = ops.mvproj_loss_fwdbwd(t['cams'], t['inv_cams'], t['joints'], t['real'], t['radii'], is_mv)
         assert rel_err(loss3[0].item(), g['loss_mv%d' % is_mv]) < 1e-4
         assert rel_err(grad.cpu(), g['grad_mv%d' % is_mv]) < 1e-4
+        assert elem_err(grad.cpu(), g['grad_mv%d' % is_mv]) < 1e-3, elem_err(grad.cpu(), g['grad_mv%d' % is_mv])
         assert rel_err(proj.cpu(), g['projected_dms']) < 1e-4
         # and against the oracle (separate terms)
         tc = {k: torch.from_numpy(v) for k, v in g.items() if v.dtype == np.float32}
@@ -150,6 +175,7 @@ def test_pose_losses_golden(S):
     cams, joints = cu(g['cams']), cu(g['joints'])
     l, gr = ops.pose_losses_fwdbwd(cams, joints, 1)
     assert rel_err(l[0].item(), g['cons']) < 1e-4 and rel_err(gr[0].cpu(), g['cons_grad']) < 1e-4
+    assert elem_err(gr[0].cpu(), g['cons_grad']) < 1e-3
     l, gr = ops.pose_losses_fwdbwd(cams, (joints * 0.5).contiguous(), 2)
     assert rel_err(l[1].item(), g['col']) < 1e-4 and rel_err(gr[1].cpu() * 0.5, g['col_grad']) < 1e-4
     assert (gr[1][:, 1:] == 0).all()                               # view-0-only quirk
@@ -173,6 +199,7 @@ def test_vae_prior_golden():
     loss3, grad = ops.vae_prior_fwdbwd(x, cu(g['eps']), blob)
     assert rel_err(loss3[0].item(), g['loss']) < 1e-4
     assert rel_err(grad.cpu().reshape(g['grad'].shape), g['grad']) < 1e-4
+    assert elem_err(grad.cpu().reshape(g['grad'].shape), g['grad']) < 1e-3
     # M not a multiple of the 4-row CTA tile
     xo = torch.from_numpy(g['x']).reshape(-1, 123)[:5].clone().requires_grad_(True)
     lo = losses.vae_prior_loss(xo, w, torch.from_numpy(g['eps'])[:5])

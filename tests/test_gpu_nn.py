@@ -286,3 +286,29 @@ def test_hourglass_golden(stacks):
         assert worst[0][0] < 2e-2, worst[0]
         med = float(np.median([w[2] for w in worst]))
         assert med < (0.25 if kind == 'noise' else 0.03)
+
+
+def test_hourglass_backward_uses_its_own_forward_tape():
+    """Two forwards (different batch sizes) before a backward, and a no-grad forward in between: each autograd node must
+    back-propagate through the activations of ITS forward (the tape used to be the most recent forward's)."""
+    from spherehand_b200.network.hourglass import create_hourglass_network
+    from oracle.hourglass import det_state_dict, det_uniform
+    net = create_hourglass_network(82, 1).to(DEV)
+    net.load_state_dict(det_state_dict(82, 1, seed=7))
+    x1 = torch.from_numpy(det_uniform(2 * 64 * 64, 1).reshape(2, 64, 64)).to(DEV)
+    x2 = torch.from_numpy(det_uniform(3 * 64 * 64, 2).reshape(3, 64, 64)).to(DEV)
+    w = torch.from_numpy(det_uniform(2 * 82 * 16 * 16, 3).reshape(2, 82, 16, 16)).to(DEV)
+    o, _ = net(x1)
+    (o[0] * w).sum().backward()
+    want = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad()
+    o1, _ = net(x1)
+    o2, _ = net(x2)                                   # a later forward with another batch size
+    with torch.no_grad():
+        net(x2)                                       # and an inference pass
+    (o1[0] * w).sum().backward()
+    for k, p in net.named_parameters():
+        assert rel_err(p.grad.cpu(), want[k].cpu()) < 1e-3, k      # same kernels, same inputs (fp32 atomics order only)
+    (o2[0] * 0.5).sum().backward()                    # the second node still has its own tape
+    with pytest.raises(RuntimeError):
+        (o2[0] * 0.5).sum().backward()
