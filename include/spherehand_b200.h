@@ -228,6 +228,10 @@ int sh_clamp_max(const void* x, long n, float max_value, void* y, void* stream);
 int sh_resize_crop(const void* depth_maps, const void* u_scales, const void* v_scales, int N, int H, int W, void* out,
                    void* stream);
 
+/* xyz[m][j][0] /= u_scales[m], xyz[m][j][1] /= v_scales[m] in place on fp32 [M,J,3]: undoes the scale augmentation on the real
+ * views' joints (network/create_network_and_criterion.py:124-126); applied to dL/dxyz it is that division's backward. */
+int sh_unscale_xy(void* xyz, const void* u_scales, const void* v_scales, int M, int J, void* stream);
+
 /* y = x * s on n fp32 elements: real_dms * depth_scale (network/engine.py:337), xyz / 100 (create_network_and_criterion.py:240). */
 int sh_scale(const void* x, float s, long n, void* y, void* stream);
 

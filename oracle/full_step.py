@@ -48,10 +48,12 @@ def synthesize(tables, poses, scales, rand_f, noise, S, depth_scale=0.01):
 
 def loss_terms(sd, stacks, images, Ns, B, V, real, cams, inv_cams, uv_t, xyz_t, radii, vae_w, eps, is_mv=True,
                depth_scale=0.01, weights=None, round_bf16=False, use=('proj', 'cons', 'prior', 'collision', 'bone'),
-               term_scale=None):
+               term_scale=None, aug=None):
     """Network + MultiTaskLoss -> (dict of weighted terms, list of projected_dms, list of real_xyz).
     term_scale(name) -> factor applied to each term as it is accumulated (names: the keys of the result plus
-    'pose_prior_recon' / 'pose_prior_kld' for the two halves of the prior); None = 1 (the reference)."""
+    'pose_prior_recon' / 'pose_prior_kld' for the two halves of the prior); None = 1 (the reference).
+    aug = (u [B*V], v [B*V]): the scale augmentation was applied to the real rows of `images`; the recovered real joints are
+    divided by it, xyz[:, :, 0] /= u, xyz[:, :, 1] /= v (create_network_and_criterion.py:124-126)."""
     w = dict(WEIGHTS)
     w.update(weights or {})
     if term_scale is not None:
@@ -67,6 +69,9 @@ def loss_terms(sd, stacks, images, Ns, B, V, real, cams, inv_cams, uv_t, xyz_t, 
     projected, xyzs = [], []
     for si, o in enumerate(outs):
         xyz = ol.soft_argmax_xyz(o[:, :J], o[:, J:], depth_scale)
+        if aug is not None:
+            div = torch.stack([aug[0], aug[1], torch.ones_like(aug[0])], dim=-1)[:, None, :]
+            xyz = torch.cat([xyz[:Ns], xyz[Ns:] / div], 0)
         if Ns:
             t['synt_uv'] = t['synt_uv'] + w['synt_hm'] * F.mse_loss(o[:Ns, :J], uv_t)
             t['synt_d'] = t['synt_d'] + w['synt_pt'] * F.mse_loss(xyz[:Ns, :, 2], xyz_t[:, :, 2])
@@ -95,17 +100,22 @@ def train_step(sd, stacks, tables, vae_w, batch, S, opt_state=None, lr=1e-4, wei
                depth_scale=0.01, round_bf16=False, apply_update=True):
     """One whole step.  `sd`: dict name -> leaf tensors (requires_grad) updated IN PLACE by Adam.
     batch: dict(real [B,V,S,S], cams, inv_cams, poses [Ns,26], scales [Ns,3], rand_f [Ns], noise [3,Ns,S,S],
-                eps [stacks,B*V,32]).  Returns (terms dict of floats incl. 'total', grads dict, aux dict)."""
+                eps [stacks,B*V,32][, aug_u, aug_v [B*V]: scale augmentation of the real views]).  Returns (terms dict of floats incl. 'total', grads dict, aux dict)."""
     real = batch['real']
     B, V = real.shape[:2]
     Ns = batch['poses'].shape[0]
     with torch.no_grad():
         synt, uv_t, xyz_t = synthesize(tables, batch['poses'], batch['scales'], batch['rand_f'], batch['noise'], S, depth_scale)
-    images = torch.cat([synt, real.reshape(B * V, S, S) * depth_scale], 0)
+    real_in = real.reshape(B * V, S, S) * depth_scale
+    aug = None
+    if 'aug_u' in batch:          # HeatmapEstimationNetwork.forward with real_aug (create_network_and_criterion.py:94-102), draws injected
+        aug = (batch['aug_u'], batch['aug_v'])
+        real_in = osy.resize_crop(real_in, aug[0], aug[1]).reshape(B * V, S, S)
+    images = torch.cat([synt, real_in], 0)
     for p in sd.values():
         p.grad = None
     terms, projected, xyzs = loss_terms(sd, stacks, images, Ns, B, V, real, batch['cams'], batch['inv_cams'], uv_t, xyz_t,
-                                        tables.radii, vae_w, batch['eps'], is_mv, depth_scale, round_bf16=round_bf16)
+                                        tables.radii, vae_w, batch['eps'], is_mv, depth_scale, round_bf16=round_bf16, aug=aug)
     total = sum(v for v in terms.values() if torch.is_tensor(v))
     total.backward()
     grads = {k: p.grad.clone() for k, p in sd.items()}

@@ -11,6 +11,8 @@ reference's own compiled kernel on the GPU box.  Files (tests/golden/):
   trained_hourglass_64.npz   HourglassNet(82, 1 stack) fwd + bwd on two reference-synthesised 64x64 depth maps, trained weights
   trained_step_64.npz        the whole step at the reference's native size: HandSynthesizer -> HeatmapEstimationNetwork(16, real_aug
                              off) -> MultiTaskLoss (all heads) -> backward, B=2 tuples x V=3 mesh-rendered views + Ns=2 poses
+  trained_step_64_aug.npz    the same 64x64 step with the reference's scale augmentation on (HeatmapEstimationNetwork(real_aug=True),
+                             create_network_and_criterion.py:94-102,124-126) and the drawn (u, v) scales recorded
   trained_hourglass_128.npz  2 stacks at 128x128 (BASELINE configs 3/4 shape), N=2; weights = oracle.hourglass.two_stack_from_trained
   trained_step_128.npz       the whole step at 128x128, 2 stacks, heatmap_size=32, B=2, V=3, Ns=2
 """
@@ -129,16 +131,28 @@ def main():
         extra.update({('gradnorm.' + k): v.grad.double().norm() for k, v in named.items()})
         save(name, x=x, **{'score%d' % i: o for i, o in enumerate(outs)}, **{'latent%d' % i: o for i, o in enumerate(lats)}, **extra)
 
-    def step_fixture(name, stacks, S, hm, sd, seed):
+    def step_fixture(name, stacks, S, hm, sd, seed, aug=False):
         B, V, Ns = 2, 3, 2
         dms, uv, dh, xyz, scales, rand_f, noise = synthesise(S, hm, poses[4:4 + Ns], seed)
         cams, inv = rand_cams(B, V, seed + 1)
         real = real_views(S, poses[:B], inv)
-        net = HeatmapEstimationNetwork(hm, 0.01, 41, stacks, real_aug=False)
+        net = HeatmapEstimationNetwork(hm, 0.01, 41, stacks, real_aug=aug)
         net.hg.load_state_dict(sd)
         crit = MultiTaskLoss(True, True, True, False, True, True, True, Constant, image_size=S, heatmap_size=hm)
         net.train()
+        extra = {}
+        if aug:                                                                          # a seed whose first uniform says "augment"
+            while True:
+                torch.manual_seed(seed + 2)
+                if torch.rand(1).item() >= 0.5:
+                    break
+                seed += 1
         torch.manual_seed(seed + 2)
+        if aug:                                                                          # create_network_and_criterion.py:95-101
+            torch.rand(1)
+            rnd = torch.rand(B * V) * 0.2 + 0.75
+            extra['aug_u'] = rnd + torch.rand_like(rnd) * 0.1 - 0.05
+            extra['aug_v'] = rnd + torch.rand_like(rnd) * 0.1 - 0.05
         eps = torch.stack([torch.randn(B * V, 32) for _ in range(stacks)])               # pose_vae.py:51, one draw per stack output
         torch.manual_seed(seed + 2)
         result = net(synt_dms=dms, real_dms=real * 0.01)
@@ -158,11 +172,13 @@ def main():
              **{('real_uv_hm_max%d' % i): r.amax(dim=(-1, -2)) for i, r in enumerate(result['real_uv_hms'])},
              **{('projected_dms%d' % i): p for i, p in enumerate(proj)},
              **{('term.' + k): v for k, v in terms.items()}, loss=loss,
-             **{('grad.' + k): named[k].grad for k in pick}, **gn)
+             **{('grad.' + k): named[k].grad for k in pick}, **gn, **extra,
+             **({'real_resized_dms': result['real_resized_dms']} if aug else {}))
         return dms
 
     dms64 = step_fixture('trained_step_64', 1, 64, 16, sd1, seed=50)
     hourglass_fixture('trained_hourglass_64', 1, 64, sd1, dms64)
+    step_fixture('trained_step_64_aug', 1, 64, 16, sd1, seed=50, aug=True)
     sd2 = two_stack_from_trained(sd1)
     dms128 = step_fixture('trained_step_128', 2, 128, 32, sd2, seed=60)
     hourglass_fixture('trained_hourglass_128', 2, 128, sd2, dms128)

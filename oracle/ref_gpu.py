@@ -162,6 +162,7 @@ def main():
     ap.add_argument('--lr', type=float, default=1e-4)
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--real_aug', type=int, default=1)
+    ap.add_argument('--tf32', default='off', choices=['off', 'default'], help="'default': torch's own flags, as the reference runs (cuDNN TF32 convolutions)")
     ap.add_argument('--weights', default='', help="'trained': pretrained/synthetic.pth (1 stack only)")
     ap.add_argument('--dump', default='', help='write the first step\'s loss terms + joints to this .npz')
     args = ap.parse_args()
@@ -170,8 +171,9 @@ def main():
         return run_engine(args)
     import numpy as np
     import torch
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.allow_tf32 = False
+    if args.tf32 == 'off':                         # strict fp32; 'default' leaves torch's flags alone (cuDNN convolutions: TF32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
     dev = torch.device('cuda', 0)
     torch.cuda.set_device(dev)
     from network.constants import Constant
@@ -245,7 +247,7 @@ def main():
     images = Ns + B * V
     out = dict(impl='gpu_reference' if args.mode == 'stock' else 'dropin', mode=args.mode, value=images / (ms * 1e-3), unit='images/s',
                ms_per_step=ms, wall_ms_per_step=wall * 1e3 / max(args.steps, 1), images_per_step=images, B=B, V=V, Ns=Ns, S=S, stacks=args.stacks,
-               steps=args.steps, warmup=args.warmup, per_step_sync=bool(args.sync), real_aug=bool(args.real_aug), dtype='f32, TF32 off' if args.mode == 'stock' else 'bf16 hourglass / f32 heads',
+               steps=args.steps, warmup=args.warmup, per_step_sync=bool(args.sync), real_aug=bool(args.real_aug), dtype=('f32, TF32 off' if args.tf32 == 'off' else 'f32, torch default flags (cuDNN convolutions in TF32)') if args.mode == 'stock' else 'bf16 hourglass / f32 heads',
                peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, note=note + ('body of network/engine.py:349-376 over the %s modules' % (
                    'unmodified reference (oracle/_ref/reference, eager PyTorch + its own CUDA rasteriser)' if args.mode == 'stock'
                    else 'reference-named modules of spherehand_b200.install()')),

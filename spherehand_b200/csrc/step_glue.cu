@@ -52,16 +52,18 @@ __global__ void __launch_bounds__(256) step_combine_kernel(
     if ((threadIdx.x & 31) == 0 && sq != 0.f) atomicAdd(&s_red[0], sq);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const float synt_d = Ns > 0 ? w.synt_pt * s_red[0] / (float)(Ns * J) : 0.f;
+        const float synt_d = Ns > 0 ? w.synt_pt * mean_scale * s_red[0] / (float)(Ns * J) : 0.f;
         if (synt_d != 0.f) { atomicAdd(&terms[1], synt_d); atomicAdd(&terms[8], synt_d); }
         if (blockIdx.x == 0) {
             float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (sse2) {
-                if (Ns > 0) t[0] = w.synt_hm * (float)(sse2[0] / ((double)Ns * J * hw));
-                if (M > 0) t[4] = w.hm_mean * (float)(sse2[1] / ((double)M * J * hw));
+                if (Ns > 0) t[0] = w.synt_hm * mean_scale * (float)(sse2[0] / ((double)Ns * J * hw));
+                if (M > 0) t[4] = w.hm_mean * mean_scale * (float)(sse2[1] / ((double)M * J * hw));
             }
-            if (loss_mv3) t[2] = w.proj * loss_mv3[0];
-            if (loss_pose3) { t[3] = w.cons * loss_pose3[0]; t[6] = w.col * loss_pose3[1]; t[7] = w.bone * loss_pose3[2]; }
+            // batch-MEAN terms carry mean_scale = 1 / world_size (like their gradients), batch-SUM terms (collision; the VAE's KLD,
+            // split inside its kernel) do not: the SUM over ranks of terms[] is then the loss of the global batch
+            if (loss_mv3) t[2] = w.proj * mean_scale * loss_mv3[0];
+            if (loss_pose3) { t[3] = w.cons * mean_scale * loss_pose3[0]; t[6] = w.col * loss_pose3[1]; t[7] = w.bone * mean_scale * loss_pose3[2]; }
             if (loss_prior3) t[5] = w.prior * loss_prior3[0];
             float tot = 0.f;
             for (int k = 0; k < 8; ++k) {
@@ -106,7 +108,26 @@ __global__ void scale_scalar_kernel(const float* __restrict__ x, float s, long n
     if (i < n) y[i] = x[i] * s;
 }
 
+// xyz[m][j][0] /= u[m], xyz[m][j][1] /= v[m] (IEEE division, as torch's): the undo of the scale augmentation on the real views'
+// joints, create_network_and_criterion.py:124-126 -- and, applied to the gradient, its backward (d(x/u)/dx = 1/u).
+__global__ void unscale_xy_kernel(float* __restrict__ xyz, const float* __restrict__ u, const float* __restrict__ v, int M, int J) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * J) return;
+    const int m = i / J;
+    xyz[3 * i] = __fdiv_rn(xyz[3 * i], u[m]);
+    xyz[3 * i + 1] = __fdiv_rn(xyz[3 * i + 1], v[m]);
+}
+
 }  // namespace
+
+SH_EXPORT int sh_unscale_xy(void* xyz, const void* u_scales, const void* v_scales, int M, int J, void* stream) {
+    SH_REQUIRE(M >= 0 && J >= 1, "sh_unscale_xy: bad arguments");
+    if (M == 0) return SH_OK;
+    SH_REQUIRE(xyz && u_scales && v_scales, "sh_unscale_xy: null pointer");
+    unscale_xy_kernel<<<sh_div_up(M * J, 256), 256, 0, (cudaStream_t)stream>>>((float*)xyz, (const float*)u_scales, (const float*)v_scales, M, J);
+    SH_CHECK_LAUNCH("unscale_xy_kernel");
+    return SH_OK;
+}
 
 SH_EXPORT int sh_step_combine(const void* g_mvproj, const void* g_pose3, const void* g_prior, const void* xyz,
                               const void* target_xyz4, const void* loss_mv3, const void* loss_pose3,

@@ -10,9 +10,18 @@ Adam step — issued as one static sequence of C-ABI kernel launches and replaye
 torch is used for device memory, streams, RNG draws (same draws, same order as the reference: SURVEY §7.3-9), CUDA-graph
 capture and the NCCL gradient all-reduce; every arithmetic kernel is in libspherehand_b200.so.  There is no CPU path.
 
-Data parallelism: tuples and synthetic poses shard across ranks; one all-reduce(SUM) of the flat fp32
-gradient per step.  Batch-MEAN loss terms are pre-scaled by 1/world_size and batch-SUM terms (collision, VAE KLD) are
-not, so the summed gradient equals the single-GPU gradient at the global batch.
+Scale augmentation (`real_aug=True`, what the reference's Engine trains with: HeatmapEstimationNetwork(real_aug=True),
+create_network_and_criterion.py:94-102,124-126): with probability 1/2 per step every real view is resized by its own
+(u, v) scale and pasted on an all-ones canvas before the network, and the recovered x / y of its joints are divided by
+(u, v).  The draws live in static device buffers (ones when the step does not augment), the resize and the two divisions
+(values and gradient) are kernels of the static launch sequence, so the captured graph replays either case.
+
+Data parallelism: tuples and synthetic poses shard across ranks; the flat fp32 gradient is all-reduced (SUM)
+in buckets that follow the backward pass: stack k's parameters are final when its backward ends, so their all-reduce runs
+on a communication stream underneath the rest of the backward pass, and only the trunk's bucket is exposed.  With
+`use_graph` the forward / backward, the collectives and Adam are ONE captured CUDA graph.  Batch-MEAN loss terms are
+pre-scaled by 1/world_size and batch-SUM terms (collision, VAE KLD) are not, so the summed gradient equals the single-GPU
+gradient at the global batch and the summed terms (`loss_dict(reduce=True)`) are its loss values.
 """
 import torch
 
@@ -34,7 +43,8 @@ class SelfSupTrainStep:
 
     def __init__(self, net, hand, vae_blob, B, V, Ns, S, depth_scale=0.01, lr=1e-4, weight_decay=1e-5,
                  weights=None, use_prior=True, use_collision=True, use_bone_length=True, use_mv_projection=True,
-                 use_mv_consistency=True, world_size=1, process_group=None, use_graph=True):
+                 use_mv_consistency=True, world_size=1, process_group=None, use_graph=True, real_aug=False,
+                 allreduce=None, bucketed=True):
         if not isinstance(net, HourglassNet):
             raise TypeError('net must be a spherehand_b200 HourglassNet')
         if S not in _LATTICE:
@@ -52,6 +62,11 @@ class SelfSupTrainStep:
         self.flags = dict(prior=use_prior and vae_blob is not None, collision=use_collision, bone=use_bone_length,
                           proj=use_mv_projection, cons=use_mv_consistency)
         self.world_size, self.pg = world_size, process_group
+        # allreduce(tensor): the collective (default: torch.distributed SUM over `process_group`); a test may inject its own
+        self._allreduce_fn = allreduce if allreduce is not None else (
+            lambda t: parallel.allreduce_gradients(t, self.world_size, self.pg))
+        self.bucketed = bucketed and world_size > 1
+        self.real_aug = bool(real_aug)
         self.use_graph = use_graph
         self.betas, self.eps_adam, self.weight_decay = (0.9, 0.999), 1e-8, weight_decay
         f32 = dict(device=dev, dtype=torch.float32)
@@ -65,6 +80,10 @@ class SelfSupTrainStep:
         self.rand_f = torch.ones((Ns,), **f32)
         self.noise = torch.zeros((3, Ns, S, S), **f32)
         self.vae_eps = torch.zeros((net.num_stacks, B * V, 32), **f32)
+        self.aug_u = torch.ones((B * V,), **f32)                        # scale augmentation of the real views (ones = none)
+        self.aug_v = torch.ones((B * V,), **f32)
+        self.augmented = False
+        self._real_scaled = torch.empty((B * V, S, S), **f32) if self.real_aug else None
         # ---- state
         self.images = torch.zeros((self.N, S, S), **f32)
         self.terms = torch.zeros(9, **f32)
@@ -78,6 +97,7 @@ class SelfSupTrainStep:
         self._graphs = {}
         self._staging = None                                   # prefetch_batch / commit_batch
         self._side = torch.cuda.Stream(device=dev)             # the VAE prior runs here, under the projection loss
+        self._comm = torch.cuda.Stream(device=dev)             # gradient buckets are all-reduced here, under the backward pass
         self.launches_per_step = None
 
     # ------------------------------------------------------------------ host-side plumbing
@@ -135,6 +155,18 @@ class SelfSupTrainStep:
         self.scales.uniform_(0.85, 0.95, generator=g)
         self.rand_f.uniform_(0.9, 1.1, generator=g)
         self.noise.normal_(generator=g)
+        if self.real_aug:
+            # HeatmapEstimationNetwork.forward (:94-102): one host uniform decides whether this step augments, then the common
+            # scale and the u / v jitter per real view
+            self.augmented = bool(torch.rand(1).item() >= 0.5)
+            if self.augmented:
+                self.aug_u.uniform_(0.0, 1.0, generator=g).mul_(0.2).add_(0.75)                  # rnd_scale
+                self.aug_v.copy_(self.aug_u)
+                self.aug_u.add_(torch.rand(self.aug_u.shape, device=self.dev, generator=g) * 0.1 - 0.05)
+                self.aug_v.add_(torch.rand(self.aug_v.shape, device=self.dev, generator=g) * 0.1 - 0.05)
+            else:
+                self.aug_u.fill_(1.0)
+                self.aug_v.fill_(1.0)
         self.vae_eps.normal_(generator=g)
 
     # ------------------------------------------------------------------ the step
@@ -156,8 +188,12 @@ class SelfSupTrainStep:
         uvd = ops.lbs_fwd(mats, *hand.kp_csr, right_hand=True, mode=1, cam=(hm / 2, hm / 2, hm / 300, hm / 300),
                           rand_f=self.rand_f)
         uv_t, _d_t, xyz_t = ops.heatmap_render(uvd, hm)
-        # ---- real branch input: real_dms * depth_scale (engine.py:337)
-        ops.scale(self.real, self.depth_scale, self.images[Ns:])
+        # ---- real branch input: real_dms * depth_scale (engine.py:337), then the scale augmentation (a scale of 1 is the identity)
+        if self.real_aug:
+            ops.scale(self.real, self.depth_scale, self._real_scaled)
+            ops.resize_crop(self._real_scaled, self.aug_u, self.aug_v, out=self.images[Ns:])
+        else:
+            ops.scale(self.real, self.depth_scale, self.images[Ns:])
         # ---- network
         scores, _latents = net.run_forward(self.images)
         # ---- heads, per stack output
@@ -168,6 +204,8 @@ class SelfSupTrainStep:
         gscores, projected = [], []
         for si, score in enumerate(scores):
             xyz, sse = ops.softargmax_fwd(score, J, Ns, uv_t, 1.0 / self.depth_scale, want_sse=True)
+            if self.real_aug:
+                ops.unscale_xy(xyz[Ns:], self.aug_u, self.aug_v)         # xyz[:, :, 0] /= u, xyz[:, :, 1] /= v  (:124-126)
             joints = xyz[Ns:].view(B, V, J, 3)
             loss_mv = g_mv = loss_p = g_p = loss_v = g_v = None
             joined = None
@@ -197,6 +235,8 @@ class SelfSupTrainStep:
             ops.step_combine(xyz, Ns, M, J, hw, w8, gxyz, self.terms, g_mvproj=g_mv, g_pose3=g_p, g_prior=g_v,
                              target_xyz4=xyz_t, loss_mv3=loss_mv, loss_pose3=loss_p, loss_prior3=loss_v, sse2=sse,
                              mean_scale=ms)
+            if self.real_aug:
+                ops.unscale_xy(gxyz[Ns:], self.aug_u, self.aug_v)        # backward of the two divisions
             gscore = torch.empty_like(score)
             if score.shape[1] != 2 * J:
                 gscore.zero_()
@@ -205,7 +245,16 @@ class SelfSupTrainStep:
                                c_real=2.0 * w['hm_mean'] * ms / (M * J * hw) if M else 0.0, out=gscore)
             gscores.append(gscore)
         self.projected_dms = projected
-        net.run_backward(gscores)
+        net.run_backward(gscores, on_bucket=self._reduce_bucket if self.bucketed else None)
+        if self.bucketed:
+            torch.cuda.current_stream(self.dev).wait_stream(self._comm)      # every bucket has been reduced
+
+    def _reduce_bucket(self, lo, hi):
+        """Called by the backward pass when flat_grad[lo:hi] is final: all-reduce it on the communication stream."""
+        main = torch.cuda.current_stream(self.dev)
+        self._comm.wait_stream(main)
+        with torch.cuda.stream(self._comm):
+            self._allreduce_fn(self.net._flat_grad[lo:hi])
 
     def _optimizer(self):
         net = self.net
@@ -213,7 +262,8 @@ class SelfSupTrainStep:
                           self.betas[0], self.betas[1], self.eps_adam, self.weight_decay)
 
     def _allreduce(self):
-        parallel.allreduce_gradients(self.net._flat_grad, self.world_size, self.pg)
+        if self.world_size > 1 and not self.bucketed:
+            self._allreduce_fn(self.net._flat_grad)
 
     def _capture(self, is_mv):
         """Warm up eagerly on a side stream (lazy CUDA init, cudaFuncSetAttribute, allocator), then capture."""
@@ -224,19 +274,21 @@ class SelfSupTrainStep:
         with torch.cuda.stream(side):
             for _ in range(2):
                 self._forward_backward(is_mv)
+                self._allreduce()
                 self._optimizer()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         # the warm-up steps must not count as training
         self.net._flat.copy_(flat0); self.adam_m.copy_(m0); self.adam_v.copy_(v0); self.step_dev.copy_(step0)
-        g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        # ONE graph: forward / backward, the gradient collectives (NCCL kernels are capturable) and Adam
+        g = torch.cuda.CUDAGraph()
         n0 = _lib.lib().sh_launch_count()
-        with torch.cuda.graph(g_fb):
+        with torch.cuda.graph(g):
             self._forward_backward(is_mv)
-        with torch.cuda.graph(g_opt, pool=g_fb.pool()):
+            self._allreduce()
             self._optimizer()
         self.launches_per_step = _lib.lib().sh_launch_count() - n0     # kernels of this library inside one step
-        return g_fb, g_opt
+        return g
 
     def step(self, is_mv=True):
         """One optimisation step on the buffers filled by load_batch / draw_randoms.  Returns the device tensor of the
@@ -249,10 +301,7 @@ class SelfSupTrainStep:
         key = bool(is_mv)
         if key not in self._graphs:
             self._graphs[key] = self._capture(is_mv)
-        g_fb, g_opt = self._graphs[key]
-        g_fb.replay()
-        self._allreduce()
-        g_opt.replay()
+        self._graphs[key].replay()
         return self.terms
 
     # ------------------------------------------------------------------ checkpoints (reference format)
@@ -303,6 +352,37 @@ class SelfSupTrainStep:
         self.step_dev.fill_(steps.pop() if steps else 0)
         self.set_lr(opt.param_groups[0]['lr'])
 
-    def loss_dict(self):
-        t = self.terms.tolist()
-        return dict(zip(TERM_NAMES, t))
+    def loss_dict(self, reduce=True):
+        """The 9 weighted loss terms as floats.  Under data parallelism each rank's terms are already scaled by the reduction rule
+        of the term (batch-MEAN terms by 1/world_size, batch-SUM terms not), so their SUM over ranks (reduce=True: one tiny
+        all-reduce, a collective every rank must enter) is the loss of the global batch; reduce=False gives this rank's share."""
+        t = self.terms.clone()
+        if reduce and self.world_size > 1:
+            parallel.allreduce_terms(t, self.world_size, self.pg)
+        return dict(zip(TERM_NAMES, t.tolist()))
+
+    def step_lr(self, step_size, gamma=0.1):
+        """torch.optim.lr_scheduler.StepLR(optimizer, step_size, gamma) of the reference (engine.py:98-99: step_size = epochs // 3,
+        gamma = 0.1) for the fused optimiser: `.step()` once per epoch moves the device-side learning rate, no re-capture."""
+        return StepLR(self, step_size, gamma)
+
+
+class StepLR:
+    """lr = base_lr * gamma ** (epoch // step_size), epoch counted by `.step()` calls (torch.optim.lr_scheduler.StepLR)."""
+
+    def __init__(self, train_step, step_size, gamma=0.1, last_epoch=0):
+        if step_size < 1:
+            raise ValueError('step_size must be >= 1 (the reference divides the epoch count by 3: needs >= 3 epochs)')
+        self.train_step, self.step_size, self.gamma = train_step, int(step_size), float(gamma)
+        self.base_lr = train_step.lr
+        self.last_epoch = int(last_epoch)
+        if last_epoch:
+            train_step.set_lr(self.get_lr())
+
+    def get_lr(self):
+        return self.base_lr * self.gamma ** (self.last_epoch // self.step_size)
+
+    def step(self):
+        self.last_epoch += 1
+        self.train_step.set_lr(self.get_lr())
+        return self.train_step.lr

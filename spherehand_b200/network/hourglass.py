@@ -188,17 +188,61 @@ class HourglassNet(nn.Module):
         self._last_run = ctx
         return scores, latents
 
-    def run_backward(self, grad_scores, run=None):
+    def grad_buckets(self):
+        """Contiguous slices of the flat gradient in the order the backward pass FINISHES them:
+        [('stack k', lo, hi, rows3) for k = last .. 0] + [('rest', ...)]: `hg.k` is final when stack k's backward ends (its
+        3x3 weight gradients after their rows `rows3` = (first, count) of the unpack table have been unpacked); everything else
+        (the trunk and the small per-stack heads that sit behind the hourglasses in the buffer) when the whole pass ends."""
+        self.pack_all_weights()
+        out = []
+        convs3 = [c for c in self.modules() if isinstance(c, nn.Conv2d) and c is not self.conv1 and c.weight.shape[-1] == 3]
+        for k in reversed(range(self.num_stacks)):
+            ps = list(self.hg[k].parameters())
+            lo = self._offsets[id(ps[0])][0]
+            hi = self._offsets[id(ps[-1])][0] + _ceil(ps[-1].numel(), 4)
+            mine = {id(c) for c in self.hg[k].modules() if isinstance(c, nn.Conv2d)}
+            rows = [i for i, c in enumerate(convs3) if id(c) in mine]
+            assert rows == list(range(rows[0], rows[0] + len(rows)))
+            out.append(('stack %d' % k, lo, hi, (rows[0], len(rows))))
+        return out
+
+    def run_backward(self, grad_scores, run=None, on_bucket=None):
         """grad_scores: list of fp32 [N,num_outputs,h,w] (or None) -> gradients accumulated into the flat grad buffer.
-        run: the tape of the forward pass to differentiate (default: the most recent run_forward)."""
+        run: the tape of the forward pass to differentiate (default: the most recent run_forward).
+        on_bucket(lo, hi): called as soon as flat_grad[lo:hi] is final (see grad_buckets; the slices together cover the buffer),
+        so a data-parallel caller can all-reduce that bucket underneath the rest of the pass."""
         run = run if run is not None else self._last_run
         if run is None:
             raise RuntimeError('run_backward: no recorded forward pass (the last forward ran with gradients disabled)')
         self._flat_grad.zero_()
         self._wg3_scratch.zero_()
-        run.backward(grad_scores)
-        if self._wg3_table.shape[0]:
-            ops.unpack_wgrad_batch(self._wg3_table, self._wg3_scratch, self._flat_grad)
+        if on_bucket is None:
+            run.backward(grad_scores)
+            if self._wg3_table.shape[0]:
+                ops.unpack_wgrad_batch(self._wg3_table, self._wg3_scratch, self._flat_grad)
+            return self._flat_grad
+        buckets = {int(name.split()[1]): (lo, hi, rows) for name, lo, hi, rows in self.grad_buckets()}
+        done = []
+
+        def stack_done(k):
+            lo, hi, (r0, nr) = buckets[k]
+            ops.unpack_wgrad_batch(self._wg3_table[r0:r0 + nr], self._wg3_scratch, self._flat_grad)
+            done.append((r0, nr))
+            on_bucket(lo, hi)
+        run.backward(grad_scores, stack_done)
+        # the remaining 3x3 layers (trunk, res.k), then the two slices around the hourglass block
+        taken = sorted(done)
+        n3, r = self._wg3_table.shape[0], 0
+        for r0, nr in taken + [(n3, 0)]:
+            if r0 > r:
+                ops.unpack_wgrad_batch(self._wg3_table[r:r0], self._wg3_scratch, self._flat_grad)
+            r = r0 + nr
+        lo_all = min(b[0] for b in buckets.values())
+        hi_all = max(b[1] for b in buckets.values())
+        if lo_all > 0:
+            on_bucket(0, lo_all)
+        if hi_all < self._flat_grad.numel():
+            on_bucket(hi_all, self._flat_grad.numel())
         return self._flat_grad
 
 
@@ -438,7 +482,7 @@ class _Run:
             if not last:
                 x = xn
 
-        def backward(grad_scores):
+        def backward(grad_scores, stack_done=None):
             dx_next = None            # gradient w.r.t. the input of the following stack
             for i in reversed(range(net.num_stacks)):
                 hg_b, res_b, fc_b, fcgn_b, sc_b, fcu_b, scu_b, xin, yres, hh = stack_b[i]
@@ -468,6 +512,8 @@ class _Run:
                     self.cs_done(xin)
                     dxin = tmp
                 dx_next = dxin
+                if stack_done is not None:
+                    stack_done(i)         # every parameter gradient of hg[i] is final
             d = l3_b(dx_next)
             d = l2_b(d)
             dl1 = torch.empty_like(l1.buf)
@@ -484,11 +530,11 @@ class _Run:
             self._t128 = torch.zeros(128, device=self.dev, dtype=torch.float32)
         return self._t128
 
-    def backward(self, grad_scores):
+    def backward(self, grad_scores, stack_done=None):
         if hasattr(self, '_t128'):
             self._t128.zero_()
         self._gn_arena = torch.zeros(max(self._gn_words, 1), device=self.dev, dtype=torch.float32)
-        self._backward(grad_scores)
+        self._backward(grad_scores, stack_done)
 
 
 def create_hourglass_network(num_outputs, num_stacks=1):

@@ -365,9 +365,18 @@ def clamp_max(x, max_value):
     return out
 
 
-def resize_crop(depth_maps, u_scales, v_scales):
+def unscale_xy(xyz, u_scales, v_scales):
+    """In place on fp32 [M,J,3]: xyz[..., 0] /= u[m], xyz[..., 1] /= v[m]."""
+    M, J = xyz.shape[0], xyz.shape[1]
+    _call('sh_unscale_xy', _chk(xyz, name='xyz'), _chk(u_scales, name='u_scales'), _chk(v_scales, name='v_scales'), M, J, _stream())
+    return xyz
+
+
+def resize_crop(depth_maps, u_scales, v_scales, out=None):
     N, H, W = depth_maps.shape
-    out = torch.empty_like(depth_maps)
+    if out is None:
+        out = torch.empty_like(depth_maps)
+    _chk(out, name='out')
     _call('sh_resize_crop', _chk(depth_maps, name='depth_maps'), _chk(u_scales, name='u_scales'), _chk(v_scales, name='v_scales'),
           N, H, W, out.data_ptr(), _stream())
     return out

@@ -14,6 +14,18 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    """torch-on-GPU references in the parity tests are fp32: cuDNN convolutions default to TF32 (torch.backends.cudnn.allow_tf32 is
+    True out of the box), which alone moves trained-weight gradients by ~3 % (measured, gpurun_out/g1_tests.log)."""
+    import torch
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def golden(name):
     return dict(np.load(os.path.join(GOLD, name + '.npz')))
 

@@ -196,3 +196,67 @@ def test_prefetch_commit_equals_load_batch(hand_model):
         step.step(is_mv=True)
         for buf, want in zip((step.real, step.cams, step.inv_cams, step.poses), batches[k]):
             assert torch.equal(buf.cpu(), want)
+
+
+def test_two_shards_sum_to_the_global_step(hand_model):
+    """Data-parallel semantics ON THE KERNELS: the global batch split into two rank shards, each run through the fused
+    step with world_size=2 (mean_scale = 1/2 on the batch-MEAN terms, M_mean = global rows in the VAE prior, bucketed reduction
+    path, collective replaced by the identity), gradients and terms SUMMED by hand == the unsharded world_size=1 step on the whole
+    batch.  Trained weights, so the comparison is tight: same kernels on the same images, only the fp32 summation order differs."""
+    from oracle.hourglass import two_stack_from_trained  # noqa: F401  (weights recipe only)
+    B, V, Ns, S, stacks = 4, 3, 4, 64, 1
+    w1 = {k: torch.from_numpy(v) for k, v in golden('trained_weights').items()}
+    hand = HandModel.from_arrays(hand_model, DEV)
+    vae_sd = {k: torch.from_numpy(v) for k, v in golden('pose_vae').items()}
+    blob = ops.vae_blob_from_state_dict(vae_sd, DEV)
+    gen = torch.Generator().manual_seed(11)
+    real, cams, inv = data.synthetic_real_batch(hand, B, V, S, gen)
+    poses = data.random_poses(Ns, gen)
+    torch.manual_seed(5)
+    draws = dict(scales=torch.rand(Ns, 3, device=DEV) * 0.1 + 0.85, rand_f=torch.rand(Ns, device=DEV) * 0.2 + 0.9,
+                 noise=torch.randn(3, Ns, S, S, device=DEV), eps=torch.randn(stacks, B * V, 32, device=DEV))
+
+    def run(lo_b, hi_b, lo_s, hi_s, world):
+        net = create_hourglass_network(82, stacks).to(DEV)
+        net.load_state_dict(w1)
+        calls = []
+        st = SelfSupTrainStep(net, hand, blob, hi_b - lo_b, V, hi_s - lo_s, S, lr=0.0, use_graph=False, world_size=world,
+                              allreduce=lambda t: calls.append(t.numel()))
+        st.load_batch(real[lo_b:hi_b], cams[lo_b:hi_b], inv[lo_b:hi_b], poses[lo_s:hi_s])
+        st.scales.copy_(draws['scales'][lo_s:hi_s]); st.rand_f.copy_(draws['rand_f'][lo_s:hi_s])
+        st.noise.copy_(draws['noise'][:, lo_s:hi_s]); st.vae_eps.copy_(draws['eps'][:, lo_b * V:hi_b * V])
+        terms = st.step(is_mv=True).clone()
+        return net._flat_grad.clone(), terms, calls, net
+    g_all, t_all, calls, net = run(0, B, 0, Ns, 1)
+    assert calls == []
+    g0, t0, c0, _ = run(0, B // 2, 0, Ns // 2, 2)
+    g1, t1, c1, _ = run(B // 2, B, Ns // 2, Ns, 2)
+    assert sum(c0) == g0.numel() and len(c0) >= 3          # bucketed: hg.0 under the trunk's backward, then the two end slices
+    gs, ts = g0 + g1, (t0 + t1).cpu().numpy()
+    ta = t_all.cpu().numpy()
+    for k, a, b in zip(TERM_NAMES, ts, ta):
+        assert abs(a - b) <= (5e-2 if k in ('collision', 'bone_length') else 5e-3) * abs(b) + 1e-6, (k, a, b)
+    # same kernels on the same images; what differs is the order of the fp32 atomics (GroupNorm statistics, weight-gradient sums),
+    # which flips single bf16 roundings downstream (the run-to-run noise of same_terms)
+    err = float((gs - g_all).double().norm() / g_all.double().norm())
+    per = max(float((gs[o:o + n] - g_all[o:o + n]).double().norm() / g_all[o:o + n].double().norm().clamp_min(1e-20))
+              for p in net.parameters() for o, n in (net._offsets[id(p)],) if float(g_all[o:o + n].norm()) > 1e-6)
+    print('two shards vs global batch: whole-gradient l2 %.2e, worst tensor %.2e' % (err, per))
+    assert err < 2e-2 and per < 1e-1
+
+
+def test_step_lr_matches_torch_scheduler(hand_model):
+    """StepLR of the fused optimiser == torch.optim.lr_scheduler.StepLR (engine.py:98-99: step_size = epochs // 3, gamma 0.1); the rate
+    reaches the device-side buffer the captured graph reads."""
+    step, _, _, _ = make_step(hand_model, 1, 3, 1, 64, 1, use_graph=False, lr=1e-3)
+    sched = step.step_lr(75 // 3, 0.1)
+    p = torch.nn.Parameter(torch.zeros(1))
+    ref_opt = torch.optim.Adam([p], lr=1e-3)
+    ref = torch.optim.lr_scheduler.StepLR(ref_opt, step_size=75 // 3, gamma=0.1)
+    for epoch in range(75):
+        ref_opt.step()
+        ref.step()
+        sched.step()
+        assert abs(step.lr - ref_opt.param_groups[0]['lr']) <= 1e-12 * 1e-3, epoch
+        assert abs(float(step.lr_dev.item()) - step.lr) <= 1e-7 * step.lr
+    assert abs(step.lr - 1e-6) < 1e-12

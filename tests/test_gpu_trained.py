@@ -89,9 +89,12 @@ def test_trained_hourglass(S, stacks, hm):
         o2, _ = oh.hourglass_forward(x, sd, stacks, round_bf16=(mode == 'emul'))
         sum((o * gg).sum() for o, gg in zip(o2, gs)).backward()
         grads[mode] = {k: v.grad for k, v in sd.items()}
-    for k in g:                                                                        # that reference == the committed fixture
-        if k.startswith('grad.'):
-            assert rel_err(grads['fp32'][k[5:]].cpu(), g[k]) < 2e-3, k
+    # that reference against the committed fixture (the reference itself on CPU).  fp32 on the GPU and fp32 on the CPU agree to
+    # ~1e-4 on most tensors, but on trained weights single tensors move by up to ~3 % between the two (measured: conv1.weight at
+    # 64x64; different summation orders through near-converged GroupNorm / ReLU features), hence a median and a loose maximum
+    ref_err = sorted(l2(grads['fp32'][k[5:]], g[k]) for k in g if k.startswith('grad.'))
+    print('torch fp32 on this GPU vs the CPU fixture, per-tensor l2: median %.2e max %.2e' % (ref_err[len(ref_err) // 2], ref_err[-1]))
+    assert ref_err[len(ref_err) // 2] < 2e-3 and ref_err[-1] < 5e-2
     check_grads(ours, grads['fp32'], grads['emul'], 'trained hourglass %d' % S)
 
 
@@ -164,11 +167,12 @@ def test_trained_modules_step(hand_model, S, stacks, hm):
     assert cosw > 0.98
 
 
-@pytest.mark.parametrize('S,stacks,hm', CASES)
-def test_trained_fused_step(hand_model, S, stacks, hm):
+@pytest.mark.parametrize('S,stacks,hm,tag', [(64, 1, 16, ''), (128, 2, 32, ''), (64, 1, 16, '_aug')])
+def test_trained_fused_step(hand_model, S, stacks, hm, tag):
     """The fused CUDA-graph step (the path bench.py times) on the fixture's batch and recorded draws: synthetic branch, loss terms and
-    the flat parameter gradient against the reference's own step."""
-    f = golden('trained_step_%d' % S)
+    the flat parameter gradient against the reference's own step.  '_aug': with the reference's scale augmentation of the real views
+    (real_aug=True: resize + crop before the network, x / y of the joints divided by the scales, and the backward of both)."""
+    f = golden('trained_step_%d%s' % (S, tag))
     B, V, Ns = 2, 3, 2
     sd0 = weights(stacks)
     hand = HandModel.from_arrays(hand_model, DEV)
@@ -176,13 +180,20 @@ def test_trained_fused_step(hand_model, S, stacks, hm):
     net = create_hourglass_network(82, stacks).to(DEV)
     net.load_state_dict(sd0)
     for use_graph in (False, True):
-        step = SelfSupTrainStep(net, hand, ops.vae_blob_from_state_dict(vae_sd, DEV), B, V, Ns, S, lr=0.0, use_graph=use_graph)
+        step = SelfSupTrainStep(net, hand, ops.vae_blob_from_state_dict(vae_sd, DEV), B, V, Ns, S, lr=0.0, use_graph=use_graph,
+                                real_aug=bool(tag))
         step.load_batch(cu(f['real']), cu(f['cams']), cu(f['inv_cams']), cu(f['poses_synt']))
         step.scales.copy_(cu(f['scales'])); step.rand_f.copy_(cu(f['rand_f'])); step.noise.copy_(cu(f['noise'])); step.vae_eps.copy_(cu(f['eps']))
+        if tag:
+            step.aug_u.copy_(cu(f['aug_u'])); step.aug_v.copy_(cu(f['aug_v']))
         terms = step.step(is_mv=True).cpu().numpy().astype(np.float64)
         ours = dict(zip(TERM_NAMES, terms))
+        if tag:
+            assert torch.equal(step.images[Ns:].cpu(), torch.from_numpy(f['real_resized_dms']))     # the resized views, bit for bit
         d = (step.images[:Ns].cpu() - torch.from_numpy(f['synt_dms'])).abs()
-        assert int((d > 1e-5).sum()) <= 64 and float(d.max()) < 1e-2                  # synthetic branch == the reference's HandSynthesizer
+        # synthetic branch == the reference's HandSynthesizer up to <= 0.5 % of the pixels: triangles crossing z = 0, where the
+        # reference's 1/z blending amplifies the last-bit differences between nvcc's and gcc's contraction of the same formula
+        assert int((d > 1e-5).sum()) <= 0.005 * d.numel() and float(d.max()) < 1e-2
         print('fused %d (graph=%s) terms' % (S, use_graph), {k: '%.5g / %.5g' % (ours[k], float(f['term.' + k])) for k in TERM_NAMES[:-1]})
         # joints of OUR step are not an output of the fused path; the hinge slack comes from the module-path bound (1e-2 / 2e-2 of range)
         rng = float(f['real_xyz0'].max() - f['real_xyz0'].min())
@@ -193,6 +204,8 @@ def test_trained_fused_step(hand_model, S, stacks, hm):
     grads = {}
     batch = {k: torch.from_numpy(f[k]) for k in ('real', 'cams', 'inv_cams', 'eps', 'scales', 'rand_f', 'noise')}
     batch['poses'] = torch.from_numpy(f['poses_synt'])
+    if tag:
+        batch['aug_u'], batch['aug_v'] = torch.from_numpy(f['aug_u']), torch.from_numpy(f['aug_v'])
     for mode in ('fp32', 'emul'):
         sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
         _, grads[mode], _ = ofs.train_step(sd, stacks, ofs.HandTables(hand_model), vae_sd, batch, S, apply_update=False, round_bf16=(mode == 'emul'))
@@ -200,4 +213,4 @@ def test_trained_fused_step(hand_model, S, stacks, hm):
         if k.startswith('gradnorm.'):                                                  # the fp32 oracle is the reference (also pinned on CPU)
             assert abs(float(grads['fp32'][k[9:]].double().norm()) / float(f[k]) - 1) < 1e-3, k
     ours = {name: step.net.grad_view(p).detach().float().cpu() for name, p in step.net.named_parameters()}
-    check_grads(ours, grads['fp32'], grads['emul'], 'fused step %d' % S)
+    check_grads(ours, grads['fp32'], grads['emul'], 'fused step %d%s' % (S, tag))

@@ -92,6 +92,14 @@ def test_joint_angle_host_walk_and_generator_position():
     assert np.array_equal(o[:n], offs) and int(e[n - 1]) == used and ja.MAX_UNIFORMS == 44
     with pytest.raises(RuntimeError):
         ja.JointAngleDataset(device='cpu')
+    # __getitem__ is the reference's DataLoader-worker protocol (a CPU tensor, no CUDA touched): 256 consecutive items == the 256
+    # consecutive `__getitem__` results of the unmodified reference, bit for bit, and the generator ends where the reference leaves it
+    ds = ja.JointAngleDataset()
+    torch.manual_seed(int(g['seed']))
+    items = [ds[i] for i in range(n)]
+    assert all(not t.is_cuda and t.dtype == torch.float32 and t.shape == (26,) for t in items)
+    assert np.array_equal(torch.stack(items).numpy(), g['poses'])
+    assert np.array_equal(torch.rand(4).numpy(), g['after'])
     assert len(ja.JointAngleDataset.__mro__) and ja.JointAngleDataset.INDEX == 6 and ja.JointAngleDataset.THUMB == 22
 
 
