@@ -112,6 +112,11 @@ class ShardBatchLoader:
         n = len(self)
         order = torch.randperm(len(self.ds), generator=self.gen) if self.shuffle else torch.arange(len(self.ds))
         batches = [order[b * self.bs:(b + 1) * self.bs].tolist() for b in range(n)]
+        # slot state carried over from the previous epoch: the host runs ahead of the stream (graph replays), so the last batches'
+        # device buffers may still be waiting to be read and their H2D copies may still be in flight
+        for s in range(2):
+            self._ready[s].synchronize()                   # pinned host buffers: their last copy has left
+            self._stream.wait_event(self._consumed[s])     # device buffers: the last consumer's reads come first (no-op if never recorded)
         self._gather(0, batches[0])                        # the first batch has nothing to overlap with
         self._issue_copy(0)
         worker = None

@@ -245,6 +245,21 @@ def test_shard_batch_loader_prefetch():
             assert np.array_equal(icp[k].cpu().numpy(), ds[order[b * 4 + k]][3].astype(np.float32))
     with pytest.raises(ValueError):
         nd.ShardBatchLoader(ds, 9, device=DEV)
+    # an ODD number of batches per epoch (here one) with a consumer whose reads are still queued when the next epoch starts
+    # (the host runs ahead of the stream under graph replay): the new epoch's copies must wait for them
+    gen = torch.Generator().manual_seed(8)
+    ref_gen = torch.Generator().manual_seed(8)
+    ld1 = nd.ShardBatchLoader(ds, 5, device=DEV, shuffle=True, generator=gen)
+    got, want = [], []
+    for epoch in range(4):
+        order = torch.randperm(len(ds), generator=ref_gen).tolist()[:5]
+        for dm, jp, cp, icp in ld1:
+            torch.cuda._sleep(30_000_000)                      # ~15 ms of queued GPU work in front of the consumer's read
+            got.append(dm.clone())
+            want.append(np.stack([np.asarray(ds[i][0], np.float32) for i in order]))
+    torch.cuda.synchronize()
+    for g_, w_ in zip(got, want):
+        assert np.array_equal(g_.cpu().numpy(), w_)
 
 
 def test_pose_denoiser_against_golden_and_oracle():

@@ -298,17 +298,26 @@ def test_hourglass_backward_uses_its_own_forward_tape():
     x1 = torch.from_numpy(det_uniform(2 * 64 * 64, 1).reshape(2, 64, 64)).to(DEV)
     x2 = torch.from_numpy(det_uniform(3 * 64 * 64, 2).reshape(3, 64, 64)).to(DEV)
     w = torch.from_numpy(det_uniform(2 * 82 * 16 * 16, 3).reshape(2, 82, 16, 16)).to(DEV)
-    o, _ = net(x1)
-    (o[0] * w).sum().backward()
-    want = {k: p.grad.clone() for k, p in net.named_parameters()}
+    def l2(a, b):
+        return float((a - b).double().norm() / b.double().norm().clamp_min(1e-30))
+    runs = []
+    for _ in range(2):
+        net.zero_grad()
+        o, _ = net(x1)
+        (o[0] * w).sum().backward()
+        runs.append({k: p.grad.clone() for k, p in net.named_parameters()})
+    want = runs[0]
+    floor = {k: l2(runs[1][k], want[k]) for k in want}    # run-to-run noise of the same pass (fp32 atomics order -> bf16 flips)
     net.zero_grad()
     o1, _ = net(x1)
     o2, _ = net(x2)                                   # a later forward with another batch size
     with torch.no_grad():
         net(x2)                                       # and an inference pass
     (o1[0] * w).sum().backward()
-    for k, p in net.named_parameters():
-        assert rel_err(p.grad.cpu(), want[k].cpu()) < 1e-3, k      # same kernels, same inputs (fp32 atomics order only)
+    worst = max((l2(p.grad, want[k]) - 3 * floor[k], k) for k, p in net.named_parameters())
+    print('own-tape backward vs a plain forward/backward: worst excess over 3x the run-to-run floor', worst, 'largest floor', max(floor.values()))
+    assert worst[0] < 2e-2, worst
+    # a wrong tape (the batch-3 forward's) would not even have the right shapes; a stale one of the same shape would be ~100 % off
     (o2[0] * 0.5).sum().backward()                    # the second node still has its own tape
     with pytest.raises(RuntimeError):
         (o2[0] * 0.5).sum().backward()
