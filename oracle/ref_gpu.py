@@ -164,6 +164,7 @@ def main():
     ap.add_argument('--real_aug', type=int, default=1)
     ap.add_argument('--tf32', default='off', choices=['off', 'default'], help="'default': torch's own flags, as the reference runs (cuDNN TF32 convolutions)")
     ap.add_argument('--weights', default='', help="'trained': pretrained/synthetic.pth (1 stack only)")
+    ap.add_argument('--sections', type=int, default=0, help='1: after the timed loop, time the sections of one step (with synchronisations)')
     ap.add_argument('--dump', default='', help='write the first step\'s loss terms + joints to this .npz')
     args = ap.parse_args()
     setup(args.mode)
@@ -230,12 +231,39 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             e0.record()
-            for _ in range(args.steps):
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+            for i in range(args.steps):
                 step()
+                marks[i].record()
             e1.record()
             torch.cuda.synchronize()
+            per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
             wall = time.perf_counter() - t0
             ms = e0.elapsed_time(e1) / max(args.steps, 1)
+            sections = {}
+            if args.sections:
+                def tick(name, t=[None]):
+                    torch.cuda.synchronize()
+                    now = time.perf_counter()
+                    if t[0] is not None and name:
+                        sections[name] = sections.get(name, 0.0) + (now - t[0]) * 1e3 / 3
+                    t[0] = now
+                for _ in range(3):
+                    tick('')
+                    real_dms = orig_real * constant.depth_scale
+                    synt_dms, uv_hms, d_hms, synt_xyz = synth(poses)
+                    tick('synthesizer')
+                    optimizer.zero_grad()
+                    result = network(synt_dms=synt_dms, real_dms=real_dms)
+                    tick('network forward')
+                    loss_terms, ball_dms = criterion(result, real_target={'real_dms': orig_real, 'camera_poses': cams, 'inv_camera_poses': inv, 'is_mv': True},
+                                                     synt_target={'uv_hms': uv_hms, 'd_hms': d_hms, 'xyz_pts': synt_xyz})
+                    loss = sum(loss_terms.values())
+                    tick('criterion')
+                    loss.backward()
+                    tick('backward')
+                    optimizer.step()
+                    tick('optimizer.step')
             break
         except torch.cuda.OutOfMemoryError:
             if B <= 1:
@@ -251,7 +279,7 @@ def main():
                peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, note=note + ('body of network/engine.py:349-376 over the %s modules' % (
                    'unmodified reference (oracle/_ref/reference, eager PyTorch + its own CUDA rasteriser)' if args.mode == 'stock'
                    else 'reference-named modules of spherehand_b200.install()')),
-               torch=torch.__version__, terms={k: v for k, v in first.items() if k.startswith('term.') or k == 'loss'})
+               torch=torch.__version__, sections_ms=sections, per_step_ms=[round(x, 2) for x in per_step], terms={k: v for k, v in first.items() if k.startswith('term.') or k == 'loss'})
     if args.dump:
         np.savez(args.dump, **{k: np.asarray(v) for k, v in first.items()})
     print(json.dumps(out))

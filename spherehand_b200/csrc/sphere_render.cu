@@ -14,7 +14,6 @@
 // (no FMA contraction), so depth is bit-identical to an IEEE evaluation of render.py:31-52 and the
 // arg-min index is exact.  Work is cut by a conservative warp-level bounding-box cull: a sphere is
 // skipped for a 32x4 pixel tile only when it provably covers no pixel of the tile.
-#include <stdlib.h>
 #include "common.cuh"
 #include "sphere_common.cuh"
 
@@ -217,7 +216,6 @@ SH_EXPORT int sh_sphere_render_fwd(const void* spheres, int N, int J, int H, int
     int band = kZbufBytes / 8 / W;
     if (band > H) band = H;
     while (band > 8 && (long)N * ((H + band - 1) / band) < 3L * SH_NUM_SMS) band = (band + 1) / 2;
-    if (const char* e = getenv("SH_R2_BAND")) { const int b = atoi(e); if (b >= 1 && b <= band) band = b; }   // tuning probe
     const size_t smem = (size_t)band * W * 8 + (size_t)(W + band) * 4;
     for (int n0 = 0; n0 < N; n0 += 65535) {
         const int nn = N - n0 < 65535 ? N - n0 : 65535;
@@ -241,8 +239,7 @@ SH_EXPORT int sh_sphere_render_bwd(const void* grad_depth, const void* idx, cons
     const int px = (W % 4 == 0 && ((uintptr_t)grad_depth & 15) == 0 && ((uintptr_t)idx & 3) == 0) ? 4 : 1;
     const TileGeom g = make_geom(W, H, px);
     const int n_tiles = g.tiles_x * g.tiles_y;
-    int tpb = pick_tiles_per_block(n_tiles, N);
-    if (const char* e = getenv("SH_R2_TPB")) { const int t = atoi(e); if (t >= 1) tpb = t; }                  // tuning probe
+    const int tpb = pick_tiles_per_block(n_tiles, N);
     for (int n0 = 0; n0 < N; n0 += 65535) {
         const int nn = N - n0 < 65535 ? N - n0 : 65535;
         dim3 grid(sh_div_up(n_tiles, tpb), nn);

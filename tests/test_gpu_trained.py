@@ -8,7 +8,8 @@ noise of the hourglass the way the flat maps of random weights do, and the bound
   * loss terms          smooth terms within 5e-2 of the reference's; the two hinge terms (sums of relu over a few active sphere
                         pairs / bones, a 0.1 mm joint move shifts them by several %) are checked exactly (1e-4) against the
                         oracle on OUR joints, and against the reference within the slack the joint bound implies
-  * parameter gradients per tensor, l2: ours-vs-reference <= 1.5 x (bf16-emulation-vs-reference) + 2e-2, where the emulation is
+  * parameter gradients whole-gradient and median per-tensor l2 error vs the reference <= 1.25 x the bf16 emulation's + 1e-2 (single
+                        tensors: 2 x + 5e-2, they carry the 6-12 % run-to-run noise of the step), where the emulation is
                         torch evaluating the same graph in fp32 with bf16 rounding at the points the kernels materialise bf16
                         (oracle.hourglass round_bf16=True).  On trained weights the forward rounding alone moves single
                         tensors' gradients by 5-17 % (ReLU masks / GroupNorm statistics of near-converged features; measured
@@ -50,11 +51,14 @@ def l2(a, b):
 
 
 def check_grads(ours, ref, emul, what):
-    """ours / ref / emul: dict name -> gradient.  Per tensor: l2(ours, ref) <= 1.5 * l2(emul, ref) + 2e-2; whole-gradient cosine."""
+    """ours / ref / emul: dict name -> gradient.  The yardstick is the bf16 emulation's own error against the fp32 reference.  Two runs
+    of the SAME step already differ by 6-12 % per tensor (tools/diag_noise.py: the order of the fp32 statistics atomics flips single
+    bf16 roundings and the deep network amplifies them), so single tensors get a loose bound (2 x emulated + 5e-2) and the stable
+    aggregates the tight ones: whole-gradient l2 and the median per-tensor l2 within 1.25 x the emulation's + 1e-2, cosine >= 0.98."""
     rows = []
     for k in ref:
         e_o, e_e = l2(ours[k], ref[k]), l2(emul[k], ref[k])
-        rows.append((e_o - 1.5 * e_e, k, e_o, e_e))
+        rows.append((e_o - 2.0 * e_e, k, e_o, e_e))
     rows.sort(reverse=True)
     fo = torch.cat([torch.as_tensor(ours[k]).double().cpu().reshape(-1) for k in ref])
     fr = torch.cat([torch.as_tensor(ref[k]).double().cpu().reshape(-1) for k in ref])
@@ -64,7 +68,9 @@ def check_grads(ours, ref, emul, what):
     print('%s: whole-gradient cosine ours %.4f (emulated bf16 %.4f), l2 ours %.4f (emulated %.4f); median per-tensor l2 ours %.4f '
           '(emulated %.4f); worst vs yardstick: %s' % (what, cos, cos_e, l2(fo, fr), l2(fe, fr), float(np.median([r[2] for r in rows])),
                                                        float(np.median([r[3] for r in rows])), [(k, '%.3f' % a, '%.3f' % b) for _, k, a, b in rows[:3]]))
-    assert rows[0][0] < 2e-2, rows[0]
+    assert rows[0][0] < 5e-2, rows[0]
+    assert l2(fo, fr) <= 1.25 * l2(fe, fr) + 1e-2
+    assert float(np.median([r[2] for r in rows])) <= 1.25 * float(np.median([r[3] for r in rows])) + 1e-2
     assert cos > 0.98 and cos > cos_e - 0.01
 
 
