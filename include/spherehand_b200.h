@@ -87,6 +87,15 @@ int sh_softargmax_fwd(const void* score, int N, int Ns, int J, int C, int h, int
 int sh_softargmax_bwd(const void* score, const void* gxyz, int N, int Ns, int J, int C, int h, int w,
                       float depth_scale_inv, const void* target_uv, float c_synt, float c_real, void* gscore,
                       void* stream);
+/* The pair the fused train step uses: the forward also leaves the per-(sample, joint) scalars of the soft-argmax in
+ * aux fp32 [N,J,8] (softmax max, 1/sum, u, v, 1/(sum relu + 1e-5), d, -, -), and the backward writes d loss / d score from them
+ * pixel-major, directly as the bf16 NHWC tensor [N,h,w,Cp] (padding channels zero) the network's backward pass consumes --
+ * no fp32 NCHW score gradient, no layout-conversion launch.  Built for J = 41, Cp = 128. */
+int sh_softargmax_fwd_aux(const void* score, int N, int Ns, int J, int C, int h, int w, float depth_scale_inv,
+                          const void* target_uv, void* xyz, void* sse2, void* aux, void* stream);
+int sh_softargmax_bwd_nhwc(const void* score, const void* gxyz, const void* aux, int N, int Ns, int J, int C, int h, int w,
+                           float depth_scale_inv, const void* target_uv, float c_synt, float c_real, void* dscore, int Cp,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------ synthetic branch
  * sh_fk_fwd replaces HandTransformationMat.forward (mesh/kinematicsTransformation.py:169-177) and, when `scales`
@@ -139,8 +148,8 @@ int sh_conv_fwd(const void* x, const void* w, const void* bias, const void* resi
  * x bf16 [N,H,W,x_C]; x_C, dy_C multiples of 64; Cin <= x_C and Cout <= dy_C are the real channel counts. */
 int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout, int taps,
                   void* dw, void* stream);
-/* 3x3 weight gradient (W >= 16) accumulated into a [9][Cout][Cin] fp32 scratch (contiguous in Cin: vector reductions; zero it
- * once per step), and the one-launch transposition of every layer's scratch into the reference layout:
+/* 3x3 weight gradient accumulated into a [9][Cout][Cin] fp32 scratch (contiguous in Cin: vector reductions; zero it once per
+ * step; W >= 16: kernel-row kernel, narrower images: per-tap kernel), and the one-launch transposition of every layer's scratch into the reference layout:
  * table int32 [n,4] (device) rows = (scratch offset, grad offset, Cout, Cin) in floats; grad[co][ci][kh][kw] += scratch[tap][co][ci]. */
 int sh_conv_wgrad3x3(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout,
                      void* scratch, void* stream);

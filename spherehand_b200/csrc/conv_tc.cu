@@ -79,7 +79,10 @@ struct WgradGeom {
     int cin, cout;                 // real channel counts = extents of the [Cout,Cin,k,k] gradient tensor
     int cin_pad, cout_pad;         // GEMM extents (multiples of BNW / 128); channels beyond the tensors read as zero
     int ksplit;                    // CTAs along the pixel dimension
+    int tap_major;                 // 1: dw is the [tap][Cout][Cin] scratch of sh_conv_wgrad3x3 (contiguous in Cin: vector reductions)
 };
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d);
 
 template <int BNW>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
@@ -169,13 +172,29 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
                 tmem_ld_wait();
-                // straight into the reference layout [Cout][Cin][kh][kw]
                 if (co < g.cout) {
                     const int ci0 = ci_t * BNW + c0;
-                    float* dst = dw + ((size_t)co * g.cin + ci0) * g.taps + tap;
+                    if (g.tap_major) {
+                        // the tap-major scratch of the 3x3 layers: 32 contiguous floats per thread, eight 16-byte reductions
+                        float* dst = dw + ((size_t)tap * g.cout + co) * g.cin + ci0;
+                        if ((g.cin & 3) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (ci0 + j < g.cin) atomicAdd(dst + (size_t)j * g.taps, __uint_as_float(v[j]));
+                            for (int j = 0; j < 32; j += 4)
+                                if (ci0 + j < g.cin)
+                                    red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                               __uint_as_float(v[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (ci0 + j < g.cin) atomicAdd(dst + j, __uint_as_float(v[j]));
+                        }
+                    } else {
+                        // straight into the reference layout [Cout][Cin][kh][kw]
+                        float* dst = dw + ((size_t)co * g.cin + ci0) * g.taps + tap;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (ci0 + j < g.cin) atomicAdd(dst + (size_t)j * g.taps, __uint_as_float(v[j]));
+                    }
                 }
             }
         }
@@ -474,6 +493,47 @@ int make_act_tmap(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
 
 }  // namespace
 
+static int launch_wgrad_generic(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout, int taps,
+                                void* dw, int tap_major, cudaStream_t st) {
+    WgradGeom g;
+    g.N = N; g.H = H; g.W = W;
+    g.bw = W < 16 ? W : 16;
+    g.bh = H < kWPix / g.bw ? H : kWPix / g.bw;
+    g.bn = kWPix / (g.bw * g.bh);
+    g.tiles_w = W / g.bw; g.tiles_h = H / g.bh; g.tiles_n = (N + g.bn - 1) / g.bn;
+    g.taps = taps; g.cin = Cin; g.cout = Cout;
+    const int bnw = (x_C % 128 == 0) ? 128 : 64;
+    g.cin_pad = x_C;
+    g.cout_pad = (dy_C + 127) / 128 * 128;
+    const int out_tiles = taps * (g.cout_pad / 128) * (g.cin_pad / bnw);
+    const int total_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+    // tap-major (small 3x3 layers): one wave of CTAs -- every extra k-split is another full set of output reductions, and at these
+    // sizes the reductions, not the MMAs, are the cost
+    int ksplit = ((tap_major ? 1 : 2) * SH_NUM_SMS + out_tiles - 1) / out_tiles;
+    if (ksplit > total_tiles) ksplit = total_tiles;
+    if (ksplit < 1) ksplit = 1;
+    g.ksplit = ksplit;
+    g.tap_major = tap_major;
+    CUtensorMap tmDY, tmX;
+    int rc = make_act_tmap(&tmDY, dy, N, H, W, dy_C, g.bw, g.bh, g.bn);
+    if (rc) return rc;
+    rc = make_act_tmap(&tmX, x, N, H, W, x_C, g.bw, g.bh, g.bn);
+    if (rc) return rc;
+    dim3 grid(out_tiles, ksplit);
+    if (bnw == 128) {
+        static bool attr = false;
+        if (!attr) { SH_CUDA(cudaFuncSetAttribute(wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<128>::kTotal)); attr = true; }
+        wgrad_kernel<128><<<grid, kThreads, WgradSmem<128>::kTotal, st>>>(tmDY, tmX, g, (float*)dw);
+    } else {
+        static bool attr = false;
+        if (!attr) { SH_CUDA(cudaFuncSetAttribute(wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<64>::kTotal)); attr = true; }
+        wgrad_kernel<64><<<grid, kThreads, WgradSmem<64>::kTotal, st>>>(tmDY, tmX, g, (float*)dw);
+    }
+    SH_CHECK_LAUNCH("wgrad_kernel");
+    return SH_OK;
+}
+
+
 // Weight gradient: dw fp32 [Cout, Cin, k, k] (the reference layout) += dY^T X_shifted, accumulated atomically (zero it
 // first).  dy bf16 [N,H,W,dy_C], x bf16 [N,H,W,x_C]; Cout <= dy_C, Cin <= x_C are the real channel counts; channels
 // beyond dy_C / x_C needed to fill the 128-wide MMA tile are supplied as zeros by TMA's out-of-bounds fill.
@@ -506,55 +566,30 @@ SH_EXPORT int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, 
         if (rc) return rc;
         static bool attr1 = false;
         if (!attr1) { SH_CUDA(cudaFuncSetAttribute(wgrad1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax)); attr1 = true; }
-        const int grid1 = g1.total_tiles < SH_NUM_SMS ? g1.total_tiles : SH_NUM_SMS;
+        // every CTA ends with a full [Cout x Cin] set of reductions: on the small levels a CTA gets at least 4 pixel tiles (measured
+        // on the 8x8 level: 22 -> 17 us; larger levels already have more tiles than that per SM)
+        const int mink = 4;
+        int grid1 = (g1.total_tiles + mink - 1) / mink;
+        if (grid1 > SH_NUM_SMS) grid1 = SH_NUM_SMS;
+        if (grid1 < 1) grid1 = 1;
         const size_t smem1 = (size_t)g1.stages * g1.stage_bytes + 1024 + 512;
         wgrad1x1_kernel<<<grid1, kThreads, smem1, st>>>(tmDY, tmX, g1, (float*)dw);
         SH_CHECK_LAUNCH("wgrad1x1_kernel");
         return SH_OK;
     }
-    WgradGeom g;
-    g.N = N; g.H = H; g.W = W;
-    g.bw = W < 16 ? W : 16;
-    g.bh = H < kWPix / g.bw ? H : kWPix / g.bw;
-    g.bn = kWPix / (g.bw * g.bh);
-    g.tiles_w = W / g.bw; g.tiles_h = H / g.bh; g.tiles_n = (N + g.bn - 1) / g.bn;
-    g.taps = taps; g.cin = Cin; g.cout = Cout;
-    const int bnw = (x_C % 128 == 0) ? 128 : 64;
-    g.cin_pad = x_C;
-    g.cout_pad = (dy_C + 127) / 128 * 128;
-    const int out_tiles = taps * (g.cout_pad / 128) * (g.cin_pad / bnw);
-    const int total_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
-    int ksplit = (2 * SH_NUM_SMS + out_tiles - 1) / out_tiles;
-    if (ksplit > total_tiles) ksplit = total_tiles;
-    if (ksplit < 1) ksplit = 1;
-    g.ksplit = ksplit;
-    CUtensorMap tmDY, tmX;
-    int rc = make_act_tmap(&tmDY, dy, N, H, W, dy_C, g.bw, g.bh, g.bn);
-    if (rc) return rc;
-    rc = make_act_tmap(&tmX, x, N, H, W, x_C, g.bw, g.bh, g.bn);
-    if (rc) return rc;
-    dim3 grid(out_tiles, ksplit);
-    if (bnw == 128) {
-        static bool attr = false;
-        if (!attr) { SH_CUDA(cudaFuncSetAttribute(wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<128>::kTotal)); attr = true; }
-        wgrad_kernel<128><<<grid, kThreads, WgradSmem<128>::kTotal, st>>>(tmDY, tmX, g, (float*)dw);
-    } else {
-        static bool attr = false;
-        if (!attr) { SH_CUDA(cudaFuncSetAttribute(wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<64>::kTotal)); attr = true; }
-        wgrad_kernel<64><<<grid, kThreads, WgradSmem<64>::kTotal, st>>>(tmDY, tmX, g, (float*)dw);
-    }
-    SH_CHECK_LAUNCH("wgrad_kernel");
-    return SH_OK;
+    return launch_wgrad_generic(dy, x, N, H, W, x_C, Cin, dy_C, Cout, taps, dw, 0, st);
 }
 
-// 3x3 weight gradient into a [9][Cout][Cin] fp32 scratch (accumulated: zero it once per step), W >= 16, H >= 4.
+// 3x3 weight gradient into a [9][Cout][Cin] fp32 scratch (accumulated: zero it once per step).  W >= 16: the kernel-row kernel;
+// narrower images (the 8x8 / 4x4 levels): the per-tap kernel writing the same scratch with vector reductions.
 SH_EXPORT int sh_conv_wgrad3x3(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout,
                                void* scratch, void* stream) {
     SH_REQUIRE(dy && x && scratch, "sh_conv_wgrad3x3: null pointer");
-    SH_REQUIRE(N >= 1 && is_pow2(H) && is_pow2(W) && H >= 4 && W >= 16, "sh_conv_wgrad3x3: H >= 4, W >= 16, powers of two");
+    SH_REQUIRE(N >= 1 && is_pow2(H) && is_pow2(W) && H >= 4 && W >= 4, "sh_conv_wgrad3x3: H, W must be powers of two >= 4");
     SH_REQUIRE(x_C % 64 == 0 && dy_C % 64 == 0 && Cin >= 1 && Cin <= x_C && Cout >= 1 && Cout <= dy_C,
                "sh_conv_wgrad3x3: channel counts must be multiples of 64 in memory");
     cudaStream_t st = (cudaStream_t)stream;
+    if (W < 16) return launch_wgrad_generic(dy, x, N, H, W, x_C, Cin, dy_C, Cout, 9, scratch, 1, st);
     Wgrad3Geom g;
     g.N = N; g.H = H; g.W = W;
     g.tiles_w = W / 16; g.tiles_h = H / 4;

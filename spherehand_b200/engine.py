@@ -44,7 +44,7 @@ class SelfSupTrainStep:
     def __init__(self, net, hand, vae_blob, B, V, Ns, S, depth_scale=0.01, lr=1e-4, weight_decay=1e-5,
                  weights=None, use_prior=True, use_collision=True, use_bone_length=True, use_mv_projection=True,
                  use_mv_consistency=True, world_size=1, process_group=None, use_graph=True, real_aug=False,
-                 allreduce=None, bucketed=True):
+                 allreduce=None, bucketed=True, overlap_heads=True):
         if not isinstance(net, HourglassNet):
             raise TypeError('net must be a spherehand_b200 HourglassNet')
         if S not in _LATTICE:
@@ -96,7 +96,9 @@ class SelfSupTrainStep:
         self.projected_dms = None
         self._graphs = {}
         self._staging = None                                   # prefetch_batch / commit_batch
-        self._side = torch.cuda.Stream(device=dev)             # the VAE prior runs here, under the projection loss
+        self._side = [torch.cuda.Stream(device=dev) for _ in range(2)]     # the VAE prior runs here, under the projection loss
+        self._heads_stream = torch.cuda.Stream(device=dev)     # heads of stack k < last run here, under stack k+1's forward
+        self.overlap_heads = overlap_heads
         self._comm = torch.cuda.Stream(device=dev)             # gradient buckets are all-reduced here, under the backward pass
         self.launches_per_step = None
 
@@ -194,60 +196,94 @@ class SelfSupTrainStep:
             ops.resize_crop(self._real_scaled, self.aug_u, self.aug_v, out=self.images[Ns:])
         else:
             ops.scale(self.real, self.depth_scale, self.images[Ns:])
-        # ---- network
-        scores, _latents = net.run_forward(self.images)
-        # ---- heads, per stack output
+        # ---- network + heads.  The heads of a stack need only that stack's scores, and their result (d loss / d score) is not
+        # needed before the backward pass: the heads of every stack but the last therefore run on their own stream underneath the
+        # NEXT stack's forward pass (fork / join events = graph edges); the last stack's heads run in line.
         self.terms.zero_()
         w8 = (w['synt_hm'], w['synt_pt'], w['mv_projection'], w['mv_consistency'] if is_mv else 0.0, w['hm_mean'],
               w['prior'], w['collision'], w['bone_length'])
-        hw = hm * hm
-        gscores, projected = [], []
-        for si, score in enumerate(scores):
-            xyz, sse = ops.softargmax_fwd(score, J, Ns, uv_t, 1.0 / self.depth_scale, want_sse=True)
-            if self.real_aug:
-                ops.unscale_xy(xyz[Ns:], self.aug_u, self.aug_v)         # xyz[:, :, 0] /= u, xyz[:, :, 1] /= v  (:124-126)
-            joints = xyz[Ns:].view(B, V, J, 3)
-            loss_mv = g_mv = loss_p = g_p = loss_v = g_v = None
-            joined = None
-            if self.flags['prior']:
-                # The VAE prior is a latency chain of 14 small dense layers on M/4 CTAs: it goes out FIRST, on a side stream, and
-                # runs underneath the projection loss (which fills the GPU) instead of in front of it.  Inside the CUDA graph the
-                # fork / join events become graph edges.
-                main = torch.cuda.current_stream(self.dev)
+        ctx = dict(is_mv=is_mv, w=w, w8=w8, ms=ms, uv_t=uv_t, xyz_t=xyz_t)
+        n_stacks = net.num_stacks
+        gscores, projected, joins = [None] * n_stacks, [None] * n_stacks, []
+        main = torch.cuda.current_stream(self.dev)
+
+        def on_score(si, score):
+            if self.overlap_heads and si < n_stacks - 1:
                 fork = torch.cuda.Event()
                 fork.record(main)
-                self._side.wait_event(fork)
-                with torch.cuda.stream(self._side):
-                    x = torch.empty((M, J * 3), device=self.dev, dtype=torch.float32)
-                    ops.scale(xyz[Ns:], 0.01, x)
-                    loss_v, g_v = ops.vae_prior_fwdbwd(x, self.vae_eps[si], self.vae_blob, M_mean=M * self.world_size)
-                    joined = torch.cuda.Event()
-                    joined.record(self._side)
-            if self.flags['proj']:
-                loss_mv, proj, g_mv = ops.mvproj_loss_fwdbwd(self.cams, self.inv_cams, joints, self.real, hand.radii, is_mv)
-                projected.append(proj)
-            pf = (1 if self.flags['cons'] else 0) | (2 if self.flags['collision'] else 0) | (4 if self.flags['bone'] else 0)
-            if pf:
-                loss_p, g_p = ops.pose_losses_fwdbwd(self.cams, joints, flags=pf)
-            if joined is not None:
-                torch.cuda.current_stream(self.dev).wait_event(joined)
-            gxyz = torch.empty_like(xyz)
-            ops.step_combine(xyz, Ns, M, J, hw, w8, gxyz, self.terms, g_mvproj=g_mv, g_pose3=g_p, g_prior=g_v,
-                             target_xyz4=xyz_t, loss_mv3=loss_mv, loss_pose3=loss_p, loss_prior3=loss_v, sse2=sse,
-                             mean_scale=ms)
-            if self.real_aug:
-                ops.unscale_xy(gxyz[Ns:], self.aug_u, self.aug_v)        # backward of the two divisions
-            gscore = torch.empty_like(score)
-            if score.shape[1] != 2 * J:
-                gscore.zero_()
-            ops.softargmax_bwd(score, gxyz, J, Ns, uv_t, 1.0 / self.depth_scale,
-                               c_synt=2.0 * w['synt_hm'] * ms / (Ns * J * hw) if Ns else 0.0,
-                               c_real=2.0 * w['hm_mean'] * ms / (M * J * hw) if M else 0.0, out=gscore)
-            gscores.append(gscore)
+                self._heads_stream.wait_event(fork)
+                with torch.cuda.stream(self._heads_stream):
+                    gscores[si], projected[si] = self._heads(si, score, ctx)
+                    done = torch.cuda.Event()
+                    done.record(self._heads_stream)
+                joins.append(done)
+            else:
+                gscores[si], projected[si] = self._heads(si, score, ctx)
+        net.run_forward(self.images, on_score=on_score, want_latents=False)
+        for done in joins:
+            main.wait_event(done)
+        projected = [p for p in projected if p is not None]
         self.projected_dms = projected
         net.run_backward(gscores, on_bucket=self._reduce_bucket if self.bucketed else None)
         if self.bucketed:
             torch.cuda.current_stream(self.dev).wait_stream(self._comm)      # every bucket has been reduced
+
+    def _heads(self, si, score, ctx):
+        """MultiTaskLoss.forward for the output of stack `si` (create_network_and_criterion.py:183-263) on the current stream:
+        soft-argmax, every loss head, the weighted terms, and d loss / d score.  -> (gscore, projected_dms | None)."""
+        hand = self.hand
+        B, V, Ns, J, hm = self.B, self.V, self.Ns, self.J, self.hm
+        M, hw = B * V, hm * hm
+        w, ms, uv_t, is_mv = ctx['w'], ctx['ms'], ctx['uv_t'], ctx['is_mv']
+        fused_layout = J == 41 and score.shape[1] == 2 * J       # the NHWC backward kernel's build (the hand model's 41 spheres)
+        if fused_layout:
+            xyz, sse, aux = ops.softargmax_fwd(score, J, Ns, uv_t, 1.0 / self.depth_scale, want_sse=True, want_aux=True)
+        else:
+            xyz, sse = ops.softargmax_fwd(score, J, Ns, uv_t, 1.0 / self.depth_scale, want_sse=True)
+        if self.real_aug:
+            ops.unscale_xy(xyz[Ns:], self.aug_u, self.aug_v)         # xyz[:, :, 0] /= u, xyz[:, :, 1] /= v  (:124-126)
+        joints = xyz[Ns:].view(B, V, J, 3)
+        loss_mv = g_mv = loss_p = g_p = loss_v = g_v = proj = None
+        joined = None
+        here = torch.cuda.current_stream(self.dev)
+        if self.flags['prior']:
+            # The VAE prior is a latency chain of 14 small dense layers on M/4 CTAs: it goes out FIRST, on a side stream, and
+            # runs underneath the projection loss (which fills the GPU) instead of in front of it.  Inside the CUDA graph the
+            # fork / join events become graph edges.
+            side = self._side[si % len(self._side)]
+            fork = torch.cuda.Event()
+            fork.record(here)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                x = torch.empty((M, J * 3), device=self.dev, dtype=torch.float32)
+                ops.scale(xyz[Ns:], 0.01, x)
+                loss_v, g_v = ops.vae_prior_fwdbwd(x, self.vae_eps[si], self.vae_blob, M_mean=M * self.world_size)
+                joined = torch.cuda.Event()
+                joined.record(side)
+        if self.flags['proj']:
+            loss_mv, proj, g_mv = ops.mvproj_loss_fwdbwd(self.cams, self.inv_cams, joints, self.real, hand.radii, is_mv)
+        pf = (1 if self.flags['cons'] else 0) | (2 if self.flags['collision'] else 0) | (4 if self.flags['bone'] else 0)
+        if pf:
+            loss_p, g_p = ops.pose_losses_fwdbwd(self.cams, joints, flags=pf)
+        if joined is not None:
+            here.wait_event(joined)
+        gxyz = torch.empty_like(xyz)
+        ops.step_combine(xyz, Ns, M, J, hw, ctx['w8'], gxyz, self.terms, g_mvproj=g_mv, g_pose3=g_p, g_prior=g_v,
+                         target_xyz4=ctx['xyz_t'], loss_mv3=loss_mv, loss_pose3=loss_p, loss_prior3=loss_v, sse2=sse,
+                         mean_scale=ms)
+        if self.real_aug:
+            ops.unscale_xy(gxyz[Ns:], self.aug_u, self.aug_v)        # backward of the two divisions
+        c_synt = 2.0 * w['synt_hm'] * ms / (Ns * J * hw) if Ns else 0.0
+        c_real = 2.0 * w['hm_mean'] * ms / (M * J * hw) if M else 0.0
+        if fused_layout:
+            # d loss / d score straight into the bf16 NHWC layout the network's backward consumes (no fp32 NCHW round trip)
+            gscore = ops.softargmax_bwd_nhwc(score, gxyz, aux, J, Ns, uv_t, 1.0 / self.depth_scale, c_synt=c_synt, c_real=c_real)
+        else:
+            gscore = torch.empty_like(score)
+            if score.shape[1] != 2 * J:
+                gscore.zero_()
+            ops.softargmax_bwd(score, gxyz, J, Ns, uv_t, 1.0 / self.depth_scale, c_synt=c_synt, c_real=c_real, out=gscore)
+        return gscore, proj
 
     def _reduce_bucket(self, lo, hi):
         """Called by the backward pass when flat_grad[lo:hi] is final: all-reduce it on the communication stream."""

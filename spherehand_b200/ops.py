@@ -128,13 +128,28 @@ def vae_prior_fwdbwd(x, eps, blob, M_mean=None):
     return loss3, grad
 
 
-def softargmax_fwd(score, J, Ns=0, target_uv=None, depth_scale_inv=100.0, want_sse=False):
+def softargmax_fwd(score, J, Ns=0, target_uv=None, depth_scale_inv=100.0, want_sse=False, want_aux=False):
+    """-> (xyz [N,J,3], sse [2] f64 | None[, aux [N,J,8]: the per-(sample, joint) scalars softargmax_bwd_nhwc needs])."""
     N, C, h, w = score.shape
     xyz = torch.empty((N, J, 3), device=score.device, dtype=torch.float32)
     sse = torch.empty(2, device=score.device, dtype=torch.float64) if want_sse else None
+    if want_aux:
+        aux = torch.empty((N, J, 8), device=score.device, dtype=torch.float32)
+        _call('sh_softargmax_fwd_aux', _chk(score, name='score'), N, Ns, J, C, h, w, float(depth_scale_inv),
+              _opt(target_uv, name='target_uv'), xyz.data_ptr(), None if sse is None else sse.data_ptr(), aux.data_ptr(), _stream())
+        return xyz, sse, aux
     _call('sh_softargmax_fwd', _chk(score, name='score'), N, Ns, J, C, h, w, float(depth_scale_inv),
           _opt(target_uv, name='target_uv'), xyz.data_ptr(), None if sse is None else sse.data_ptr(), _stream())
     return xyz, sse
+
+
+def softargmax_bwd_nhwc(score, gxyz, aux, J, Ns=0, target_uv=None, depth_scale_inv=100.0, c_synt=0.0, c_real=0.0, Cp=128):
+    """d loss / d score as the bf16 NHWC tensor [N,h,w,Cp] of the network's backward pass (channels >= 2J zero)."""
+    N, C, h, w = score.shape
+    out = torch.empty((N, h, w, Cp), device=score.device, dtype=BF16)
+    _call('sh_softargmax_bwd_nhwc', _chk(score, name='score'), _chk(gxyz, name='gxyz'), _chk(aux, name='aux'), N, Ns, J, C, h, w,
+          float(depth_scale_inv), _opt(target_uv, name='target_uv'), float(c_synt), float(c_real), out.data_ptr(), Cp, _stream())
+    return out
 
 
 def softargmax_bwd(score, gxyz, J, Ns=0, target_uv=None, depth_scale_inv=100.0, c_synt=0.0, c_real=0.0, out=None):

@@ -226,6 +226,26 @@ def test_softargmax_golden():
     ref[:1, :41] += 0.3 * (score[:1, :41] - tgt)
     ref[1:, :41] += 0.7 * score[1:, :41]
     assert rel_err(gs2.cpu(), ref.cpu()) < 1e-5
+    # the fused step's pair: forward + per-(sample, joint) scalars, backward straight into bf16 NHWC [N,h,w,128]
+    xyz3, sse3, aux = ops.softargmax_fwd(score, 41, Ns=1, target_uv=tgt, want_sse=True, want_aux=True)
+    assert torch.equal(xyz3, xyz) and torch.equal(sse3, sse) and aux.shape == (3, 41, 8)
+    dn = ops.softargmax_bwd_nhwc(score, cu(g['gxyz']), aux, 41, Ns=1, target_uv=tgt, c_synt=0.3, c_real=0.7)
+    assert dn.shape == (3, 16, 16, 128) and dn.dtype == torch.bfloat16 and (dn[..., 82:] == 0).all()
+    want = gs2.permute(0, 2, 3, 1)                                         # the NCHW fp32 gradient of the two-launch path
+    got = dn[..., :82].float()
+    assert rel_err(got.cpu(), want.cpu()) < 4e-3                          # one bf16 rounding of the same fp32 values
+    assert rel_err(got.cpu(), want.to(torch.bfloat16).float().cpu()) < 1e-4 or (got != want.to(torch.bfloat16).float()).float().mean() < 1e-3
+    # a larger, ragged case (32x32 maps, 5 samples, 2 synthetic) against the same reference path
+    torch.manual_seed(2)
+    sc = (torch.randn(5, 82, 32, 32, device=DEV) * 0.3).contiguous()
+    tg2 = torch.rand(2, 41, 32, 32, device=DEV)
+    gx = torch.randn(5, 41, 3, device=DEV)
+    _, _, aux2 = ops.softargmax_fwd(sc, 41, Ns=2, target_uv=tg2, want_sse=True, want_aux=True)
+    ref2 = ops.softargmax_bwd(sc, gx, 41, Ns=2, target_uv=tg2, c_synt=1e-3, c_real=2e-5)
+    got2 = ops.softargmax_bwd_nhwc(sc, gx, aux2, 41, Ns=2, target_uv=tg2, c_synt=1e-3, c_real=2e-5)
+    assert rel_err(got2[..., :82].float().cpu(), ref2.permute(0, 2, 3, 1).cpu()) < 4e-3 and (got2[..., 82:] == 0).all()
+    with pytest.raises(Exception):
+        ops.softargmax_bwd_nhwc(sc[:, :80].contiguous(), gx[:, :40].contiguous(), aux2, 40)      # built for J = 41
 
 
 # ------------------------------------------------------------------------------------------------ synthetic branch

@@ -38,7 +38,7 @@ def stats_of(x_nhwc, G):
 
 
 @pytest.mark.parametrize('N,H,Cin,Cout,taps', [(2, 32, 128, 128, 9), (3, 16, 256, 128, 1), (2, 64, 64, 64, 9), (5, 8, 128, 256, 1),
-                                               (4, 4, 128, 128, 9), (2, 32, 256, 82, 1), (2, 32, 64, 128, 1), (3, 16, 128, 128, 9), (1, 64, 64, 64, 9)])
+                                               (4, 4, 128, 128, 9), (37, 8, 128, 128, 9), (2, 32, 256, 82, 1), (2, 32, 64, 128, 1), (3, 16, 128, 128, 9), (1, 64, 64, 64, 9)])
 def test_conv_fwd_dgrad_wgrad(N, H, Cin, Cout, taps):
     torch.manual_seed(N * 100 + H)
     k = 3 if taps == 9 else 1
@@ -84,8 +84,9 @@ def test_conv_fwd_dgrad_wgrad(N, H, Cin, Cout, taps):
     ops.conv_wgrad(dyp, nhwc(x), N, H, H, Cin, Cin, b_cols, Cout, taps, dw)
     ref_dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, padding=k // 2)
     assert rel_err(dw.cpu(), ref_dw.cpu()) < 2e-3
-    if taps == 9 and H >= 16:
-        # kernel-row formulation: [9][Cout][Cin] scratch (accumulating) + batched unpack into the reference layout (+=)
+    if taps == 9:
+        # [9][Cout][Cin] scratch (accumulating; W >= 16: kernel-row kernel, narrower: per-tap kernel with vector reductions) + batched
+        # unpack into the reference layout (+=)
         scratch = torch.zeros(9 * Cout * Cin, device=DEV)
         ops.conv_wgrad3x3(dyp, nhwc(x), N, H, H, Cin, Cin, b_cols, Cout, scratch)
         dw2 = torch.ones_like(w)
