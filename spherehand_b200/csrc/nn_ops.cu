@@ -13,6 +13,7 @@
 // a separate reduction pass; kernels that produce an output-gradient tensor optionally accumulate its per-channel
 // column sum (the bias gradient of the producing convolution).  These kernels are HBM-bound: 16-byte vector
 // accesses (8 bf16 channels per thread), grid = (chunks, N) with >= 2 waves of 148 SMs.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace {
@@ -207,7 +208,11 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__global__ void __launch_bounds__(kBT, 4) gn_relu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ x,
+// MB = resident blocks per SM the register allocation aims at: 4 with an addend (three 16 KB slabs per block: shared memory caps it
+// there anyway), 6 without (two slabs: 80 registers instead of 109 let six blocks = 24 warps share an SM; the kernel is latency-
+// bound -- neither the issue slots nor HBM are saturated -- so resident warps are what it is short of).
+template <int MB>
+__global__ void __launch_bounds__(kBT, MB) gn_relu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ x,
                                                              const float* __restrict__ stats_in, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const __nv_bfloat16* __restrict__ addend,
                                                              int HW, int C, int G, int ppb, float eps, float* __restrict__ red,
@@ -967,14 +972,23 @@ static int gn_relu_bwd_impl(const void* da, const void* x, const void* stats_in,
     const size_t smem = (size_t)ppb * C * 2 * (addend ? 3 : 2);
     static bool attr = false;
     if (!attr) {
-        SH_CUDA(cudaFuncSetAttribute(gn_relu_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kBwdSmallElems * 2));
+        SH_CUDA(cudaFuncSetAttribute(gn_relu_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kBwdSmallElems * 2));
+        SH_CUDA(cudaFuncSetAttribute(gn_relu_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kBwdSmallElems * 2));
         attr = true;
     }
     dim3 grid(nblk, N);
-    gn_relu_bwd_kernel<<<grid, kBT, smem, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)x, (const float*)stats_in,
-                                               (const float*)gamma, (const float*)beta, (const __nv_bfloat16*)addend, HW, C, G, ppb,
-                                               eps, (float*)red, (unsigned*)red + (size_t)N * G * 2, (float*)dgamma, (float*)dbeta,
-                                               (__nv_bfloat16*)dx, (float*)colsum);
+    const char* mb_env = getenv("SH_GN_BWD_MB");            // tuning probe: 4 forces the four-block build everywhere
+    const bool six = !addend && smem <= 36 * 1024 && !(mb_env && atoi(mb_env) == 4);
+    if (six)
+        gn_relu_bwd_kernel<6><<<grid, kBT, smem, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)x, (const float*)stats_in,
+                                                      (const float*)gamma, (const float*)beta, (const __nv_bfloat16*)addend, HW, C, G, ppb,
+                                                      eps, (float*)red, (unsigned*)red + (size_t)N * G * 2, (float*)dgamma, (float*)dbeta,
+                                                      (__nv_bfloat16*)dx, (float*)colsum);
+    else
+        gn_relu_bwd_kernel<4><<<grid, kBT, smem, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)x, (const float*)stats_in,
+                                                      (const float*)gamma, (const float*)beta, (const __nv_bfloat16*)addend, HW, C, G, ppb,
+                                                      eps, (float*)red, (unsigned*)red + (size_t)N * G * 2, (float*)dgamma, (float*)dbeta,
+                                                      (__nv_bfloat16*)dx, (float*)colsum);
     SH_CHECK_LAUNCH("gn_relu_bwd_kernel");
     return SH_OK;
 }

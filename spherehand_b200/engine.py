@@ -19,7 +19,7 @@ create_network_and_criterion.py:94-102,124-126): with probability 1/2 per step e
 Data parallelism: tuples and synthetic poses shard across ranks; the flat fp32 gradient is all-reduced (SUM)
 in buckets that follow the backward pass: stack k's parameters are final when its backward ends, so their all-reduce runs
 on a communication stream underneath the rest of the backward pass, and only the trunk's bucket is exposed.  With
-`use_graph` the forward / backward, the collectives and Adam are ONE captured CUDA graph.  Batch-MEAN loss terms are
+`use_graph` the step is replayed as CUDA-graph segments cut at the bucket boundaries, the NCCL calls issued between them.  Batch-MEAN loss terms are
 pre-scaled by 1/world_size and batch-SUM terms (collision, VAE KLD) are not, so the summed gradient equals the single-GPU
 gradient at the global batch and the summed terms (`loss_dict(reduce=True)`) are its loss values.
 """
@@ -172,7 +172,8 @@ class SelfSupTrainStep:
         self.vae_eps.normal_(generator=g)
 
     # ------------------------------------------------------------------ the step
-    def _forward_backward(self, is_mv):
+    def _forward_backward(self, is_mv, on_bucket=None):
+        """on_bucket(lo, hi): called by the backward pass as soon as flat_grad[lo:hi] is final (data-parallel runs)."""
         net, hand = self.net, self.hand
         B, V, Ns, S, J, hm, N = self.B, self.V, self.Ns, self.S, self.J, self.hm, self.N
         M = B * V
@@ -224,9 +225,7 @@ class SelfSupTrainStep:
             main.wait_event(done)
         projected = [p for p in projected if p is not None]
         self.projected_dms = projected
-        net.run_backward(gscores, on_bucket=self._reduce_bucket if self.bucketed else None)
-        if self.bucketed:
-            torch.cuda.current_stream(self.dev).wait_stream(self._comm)      # every bucket has been reduced
+        net.run_backward(gscores, on_bucket=on_bucket)
 
     def _heads(self, si, score, ctx):
         """MultiTaskLoss.forward for the output of stack `si` (create_network_and_criterion.py:183-263) on the current stream:
@@ -301,43 +300,97 @@ class SelfSupTrainStep:
         if self.world_size > 1 and not self.bucketed:
             self._allreduce_fn(self.net._flat_grad)
 
+    def _eager_step(self, is_mv):
+        self._forward_backward(is_mv, on_bucket=self._reduce_bucket if self.bucketed else None)
+        if self.bucketed:
+            torch.cuda.current_stream(self.dev).wait_stream(self._comm)      # every bucket has been reduced
+        self._allreduce()
+        self._optimizer()
+
     def _capture(self, is_mv):
-        """Warm up eagerly on a side stream (lazy CUDA init, cudaFuncSetAttribute, allocator), then capture."""
+        """Warm up eagerly on a side stream (lazy CUDA init, cudaFuncSetAttribute, allocator), then capture the step as a list of
+        CUDA-graph SEGMENTS with the gradient collectives between them: [('graph', g) | ('reduce', lo, hi), ...].  One GPU: a single
+        segment.  Data parallel: the backward pass is cut where a bucket of the flat gradient becomes final; at replay the bucket's
+        all-reduce is issued (an ordinary NCCL call on the communication stream) and the next segment is replayed on top of it, so
+        the collective runs underneath the rest of the backward pass.  NCCL stays OUT of the captured graphs on purpose: with
+        the collectives captured (one graph for everything) a later `dist.barrier()` never returned on this stack."""
+        import gc
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream())
         step0 = self.step_dev.clone()
         flat0, m0, v0 = self.net._flat.clone(), self.adam_m.clone(), self.adam_v.clone()
         with torch.cuda.stream(side):
             for _ in range(2):
-                self._forward_backward(is_mv)
-                self._allreduce()
-                self._optimizer()
+                self._eager_step(is_mv)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         # the warm-up steps must not count as training
         self.net._flat.copy_(flat0); self.adam_m.copy_(m0); self.adam_v.copy_(v0); self.step_dev.copy_(step0)
-        # ONE graph: forward / backward, the gradient collectives (NCCL kernels are capturable) and Adam
-        g = torch.cuda.CUDAGraph()
-        n0 = _lib.lib().sh_launch_count()
-        with torch.cuda.graph(g):
-            self._forward_backward(is_mv)
-            self._allreduce()
+        items, state = [], dict(pool=None)
+        count = _lib.lib().sh_launch_count
+
+        def begin():
+            g = torch.cuda.CUDAGraph()
+            ctx = torch.cuda.graph(g) if state['pool'] is None else torch.cuda.graph(g, pool=state['pool'])
+            ctx.__enter__()
+            state.update(g=g, ctx=ctx, n0=count())
+
+        def end():
+            state['ctx'].__exit__(None, None, None)
+            if state['pool'] is None:
+                state['pool'] = state['g'].pool()          # later segments read the activations the earlier ones wrote
+            items.append(('graph', state['g']))
+
+        def cut(lo, hi):
+            if count() != state['n0']:                      # (consecutive buckets share one cut)
+                end()
+                items.append(('reduce', lo, hi))
+                begin()
+            else:
+                items.append(('reduce', lo, hi))
+
+        # Python's cyclic collector must not run while a capture is open: collecting an old step's CUDA graph there frees its memory
+        # pool (cudaFree) and invalidates the capture ("operation failed due to a previous error during capture")
+        gc_was = gc.isenabled()
+        gc.collect()
+        gc.disable()
+        n0 = count()
+        try:
+            begin()
+            self._forward_backward(is_mv, on_bucket=cut if self.bucketed else None)
+            if self.world_size > 1 and not self.bucketed:
+                cut(0, self.net._flat_grad.numel())
             self._optimizer()
-        self.launches_per_step = _lib.lib().sh_launch_count() - n0     # kernels of this library inside one step
-        return g
+            end()
+        finally:
+            if gc_was:
+                gc.enable()
+        self.launches_per_step = count() - n0     # kernels of this library inside one step
+        return items
+
+    def _replay(self, items):
+        main = torch.cuda.current_stream(self.dev)
+        last = max(i for i, it in enumerate(items) if it[0] == 'graph')
+        reduced = False
+        for i, it in enumerate(items):
+            if it[0] == 'graph':
+                if i == last and reduced:
+                    main.wait_stream(self._comm)            # Adam reads the reduced gradient
+                it[1].replay()
+            else:
+                self._reduce_bucket(it[1], it[2])
+                reduced = True
 
     def step(self, is_mv=True):
         """One optimisation step on the buffers filled by load_batch / draw_randoms.  Returns the device tensor of the
         9 weighted loss terms (TERM_NAMES); reading it synchronises."""
         if not self.use_graph:
-            self._forward_backward(is_mv)
-            self._allreduce()
-            self._optimizer()
+            self._eager_step(is_mv)
             return self.terms
         key = bool(is_mv)
         if key not in self._graphs:
             self._graphs[key] = self._capture(is_mv)
-        self._graphs[key].replay()
+        self._replay(self._graphs[key])
         return self.terms
 
     # ------------------------------------------------------------------ checkpoints (reference format)

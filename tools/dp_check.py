@@ -1,5 +1,5 @@
-"""Data-parallel check on real GPUs (torchrun, one rank per GPU, NCCL): the bucketed gradient all-reduce inside the captured
-graph.  Every rank: identical replicas, its own shard; after a step (eager, then graph replay) the all-reduced flat gradient
+"""Data-parallel check on real GPUs (torchrun, one rank per GPU, NCCL): the bucketed gradient all-reduce underneath the backward
+pass, eager and with the step replayed as CUDA-graph segments.  Every rank: identical replicas, its own shard; after a step (eager, then graph replay) the all-reduced flat gradient
 must be bit-identical on every rank and equal to the sum of the ranks' local gradients (computed by a second replica whose
 collective is the identity and summed with one plain all_reduce); weights stay identical across ranks over several steps.
 
@@ -79,11 +79,16 @@ def main():
             print('launches per step', a.launches_per_step, flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    good = flag.item() == 1.0
     if rank == 0:
-        print('DP CHECK', 'OK' if flag.item() == 1.0 else 'FAILED', flush=True)
+        print('DP CHECK', 'OK' if good else 'FAILED', flush=True)
+    del a, b
+    torch.cuda.synchronize()
     dist.barrier()
+    if rank == 0:
+        print('barrier passed', flush=True)
     dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1.0 else 1)
+    sys.exit(0 if good else 1)
 
 
 if __name__ == '__main__':

@@ -59,9 +59,45 @@ def traffic(p1, p3, dst, note):
     print(json.dumps(out, indent=1))
 
 
+FAMILY_OF_TAG = {'sh_conv_fwd_1x1': 'conv1x1', 'sh_conv_fwd_3x3': 'conv3x3', 'sh_conv_wgrad_1x1': 'wgrad1x1', 'sh_conv_wgrad_3x3': 'wgrad3x3',
+                 'sh_conv_wgrad3x3': 'wgrad3x3', 'sh_gn_relu_fwd': 'gn_relu_fwd', 'sh_gn_relu_bwd_prezeroed': 'gn_relu_bwd', 'sh_gn_relu_bwd': 'gn_relu_bwd',
+                 'sh_maxpool_fwd': 'pool_upsample_add', 'sh_maxpool_bwd': 'pool_upsample_add', 'sh_upsample_add_fwd': 'pool_upsample_add',
+                 'sh_upsample_bwd': 'pool_upsample_add', 'sh_add': 'pool_upsample_add', 'sh_mvproj_loss_fwdbwd': 'mvproj'}
+
+
+def families(path, dst, note):
+    """Launch list taken with `--nvtx --print-nvtx-rename kernel` (kernels carry the name of the C-ABI call that launched them) and the
+    metrics gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum -> per-family DRAM traffic per launch, the file
+    bench.py reads for `roofline.traffic` (keys = bench.FAMILY_KERNELS)."""
+    names, vals = rows_of(path)
+    out = {}
+    for i, n in names.items():
+        tag = n.split('(')[0].strip()
+        fam = FAMILY_OF_TAG.get(tag)
+        if fam is None:
+            continue
+        d = out.setdefault(fam, dict(launches=0, dram_read_bytes=0.0, dram_write_bytes=0.0, total_us_under_ncu=0.0))
+        if vals[i].get('gpu__time_duration.sum', 0.0) < 3000.0 and tag in ('sh_mvproj_loss_fwdbwd',):
+            pass                                  # prep / finish kernels of the call: their bytes count, not their launch
+        else:
+            d['launches'] += 1
+        d['dram_read_bytes'] += vals[i].get('dram__bytes_read.sum', 0.0)
+        d['dram_write_bytes'] += vals[i].get('dram__bytes_write.sum', 0.0)
+        d['total_us_under_ncu'] += vals[i].get('gpu__time_duration.sum', 0.0) / 1e3
+    for fam, d in out.items():
+        d['dram_bytes_per_launch'] = (d['dram_read_bytes'] + d['dram_write_bytes']) / max(d['launches'], 1)
+        d['source'] = note
+    json.dump(out, open(dst, 'w'), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == '__main__':
     if sys.argv[1] == 'launches':
         launches(*sys.argv[2:5])
+    elif sys.argv[1] == 'families':
+        families(*sys.argv[2:5])
+    elif sys.argv[1] == 'reps':
+        reps(sys.argv[2], [tuple(a.split('=', 1)) for a in sys.argv[3:]])
     else:
         traffic(*sys.argv[2:6])
 
