@@ -303,7 +303,7 @@ def run_ours(args, rank, world, local_rank):
     blob = ops.vae_blob_from_state_dict(vae_sd, dev)
     torch.manual_seed(0)                                   # identical replicas
     net = create_hourglass_network(2 * J, STACKS).to(dev)
-    step = SelfSupTrainStep(net, hand, blob, B, V, NS, S, lr=1e-4, world_size=world, real_aug=bool(args.real_aug))
+    step = SelfSupTrainStep(net, hand, blob, B, V, NS, S, lr=1e-4, world_size=world, real_aug=bool(args.real_aug), bucketed=bool(args.bucketed))
     gen = torch.Generator().manual_seed(1234 + rank)       # each rank its own shard of the global batch
     real, cams, inv = data.synthetic_real_batch(hand, B, V, S, gen)
     poses = data.random_poses(NS, gen)
@@ -365,7 +365,7 @@ def run_ours(args, rank, world, local_rank):
                 steps=args.steps, warmup=warm, ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='bf16', data='synthetic',
                 config=dict(workload=WORKLOAD, global_images_per_step=world * IMAGES_PER_STEP, tuples_per_s=world * B * args.steps / (ms * 1e-3),
-                            parallelism='dp%d' % world, precision='bf16 operands / fp32 accumulate in the hourglass, fp32 everywhere else',
+                            parallelism='dp%d' % world, gradient_allreduce=('bucketed under the backward pass' if step.bucketed else 'one call after the backward pass') if world > 1 else 'none', precision='bf16 operands / fp32 accumulate in the hourglass, fp32 everywhere else',
                             l2='not flushed: per-step activation working set (>= 10 GB) >> 126 MB L2',
                             real_aug='on: the reference\'s scale augmentation of the real views (create_network_and_criterion.py:94-102) inside the step, '
                                      'drawn per step (50 % of the steps resize)' if args.real_aug else 'off',
@@ -483,6 +483,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--legs', type=int, default=1, help='0: skip the reference-GPU / drop-in / renderer / CPU legs (N=1 only)')
     ap.add_argument('--real_aug', type=int, default=0, help='1: the scale augmentation of the real views inside the timed step')
+    ap.add_argument('--bucketed', type=int, default=0, help='1: all-reduce the gradient in buckets underneath the backward pass instead of once after it (N > 1; measured slower)')
     ap.add_argument('--sample_poses', type=int, default=0, help='1: draw the synthetic poses on the device every step')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))

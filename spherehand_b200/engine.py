@@ -17,9 +17,12 @@ create_network_and_criterion.py:94-102,124-126): with probability 1/2 per step e
 (values and gradient) are kernels of the static launch sequence, so the captured graph replays either case.
 
 Data parallelism: tuples and synthetic poses shard across ranks; the flat fp32 gradient is all-reduced (SUM)
-in buckets that follow the backward pass: stack k's parameters are final when its backward ends, so their all-reduce runs
-on a communication stream underneath the rest of the backward pass, and only the trunk's bucket is exposed.  With
-`use_graph` the step is replayed as CUDA-graph segments cut at the bucket boundaries, the NCCL calls issued between them.  Batch-MEAN loss terms are
+once, between the backward pass and Adam (two CUDA-graph segments with the NCCL call between their replays).
+`bucketed=True` instead all-reduces in buckets that follow the backward pass (stack k's parameters are final when its
+backward ends; their all-reduce runs on a communication stream underneath the rest of the pass, graph segments cut at the
+bucket boundaries).  Measured on two B200s the bucketed form is SLOWER (13.80 vs 13.67 ms per step, 13.52 on one GPU): the
+NCCL kernels take SMs away from persistent kernels that were launched with one CTA per SM, which costs more than the 0.15 ms
+the single exposed all-reduce does.  Batch-MEAN loss terms are
 pre-scaled by 1/world_size and batch-SUM terms (collision, VAE KLD) are not, so the summed gradient equals the single-GPU
 gradient at the global batch and the summed terms (`loss_dict(reduce=True)`) are its loss values.
 """
@@ -44,7 +47,7 @@ class SelfSupTrainStep:
     def __init__(self, net, hand, vae_blob, B, V, Ns, S, depth_scale=0.01, lr=1e-4, weight_decay=1e-5,
                  weights=None, use_prior=True, use_collision=True, use_bone_length=True, use_mv_projection=True,
                  use_mv_consistency=True, world_size=1, process_group=None, use_graph=True, real_aug=False,
-                 allreduce=None, bucketed=True, overlap_heads=True):
+                 allreduce=None, bucketed=False, overlap_heads=True):
         if not isinstance(net, HourglassNet):
             raise TypeError('net must be a spherehand_b200 HourglassNet')
         if S not in _LATTICE:

@@ -200,8 +200,8 @@ def test_prefetch_commit_equals_load_batch(hand_model):
 
 def test_two_shards_sum_to_the_global_step(hand_model):
     """Data-parallel semantics ON THE KERNELS: the global batch split into two rank shards, each run through the fused
-    step with world_size=2 (mean_scale = 1/2 on the batch-MEAN terms, M_mean = global rows in the VAE prior, bucketed reduction
-    path, collective replaced by the identity), gradients and terms SUMMED by hand == the unsharded world_size=1 step on the whole
+    step with world_size=2 (mean_scale = 1/2 on the batch-MEAN terms, M_mean = global rows in the VAE prior, one shard through the bucketed
+    reduction path and one through the single all-reduce, collective replaced by the identity), gradients and terms SUMMED by hand == the unsharded world_size=1 step on the whole
     batch.  Trained weights, so the comparison is tight: same kernels on the same images, only the fp32 summation order differs."""
     from oracle.hourglass import two_stack_from_trained  # noqa: F401  (weights recipe only)
     B, V, Ns, S, stacks = 4, 3, 4, 64, 1
@@ -216,12 +216,12 @@ def test_two_shards_sum_to_the_global_step(hand_model):
     draws = dict(scales=torch.rand(Ns, 3, device=DEV) * 0.1 + 0.85, rand_f=torch.rand(Ns, device=DEV) * 0.2 + 0.9,
                  noise=torch.randn(3, Ns, S, S, device=DEV), eps=torch.randn(stacks, B * V, 32, device=DEV))
 
-    def run(lo_b, hi_b, lo_s, hi_s, world):
+    def run(lo_b, hi_b, lo_s, hi_s, world, bucketed=False):
         net = create_hourglass_network(82, stacks).to(DEV)
         net.load_state_dict(w1)
         calls = []
         st = SelfSupTrainStep(net, hand, blob, hi_b - lo_b, V, hi_s - lo_s, S, lr=0.0, use_graph=False, world_size=world,
-                              allreduce=lambda t: calls.append(t.numel()))
+                              allreduce=lambda t: calls.append(t.numel()), bucketed=bucketed)
         st.load_batch(real[lo_b:hi_b], cams[lo_b:hi_b], inv[lo_b:hi_b], poses[lo_s:hi_s])
         st.scales.copy_(draws['scales'][lo_s:hi_s]); st.rand_f.copy_(draws['rand_f'][lo_s:hi_s])
         st.noise.copy_(draws['noise'][:, lo_s:hi_s]); st.vae_eps.copy_(draws['eps'][:, lo_b * V:hi_b * V])
@@ -230,9 +230,10 @@ def test_two_shards_sum_to_the_global_step(hand_model):
     g_all, t_all, calls, net = run(0, B, 0, Ns, 1)
     assert calls == []
     g_again, t_again, _, _ = run(0, B, 0, Ns, 1)         # the run-to-run noise floor of the same step (fp32 atomics order)
-    g0, t0, c0, _ = run(0, B // 2, 0, Ns // 2, 2)
-    g1, t1, c1, _ = run(B // 2, B, Ns // 2, Ns, 2)
+    g0, t0, c0, _ = run(0, B // 2, 0, Ns // 2, 2, bucketed=True)
+    g1, t1, c1, _ = run(B // 2, B, Ns // 2, Ns, 2, bucketed=False)
     assert sum(c0) == g0.numel() and len(c0) >= 3          # bucketed: hg.0 under the trunk's backward, then the two end slices
+    assert c1 == [g1.numel()]                              # default: one all-reduce of the whole flat gradient
     gs, ts = g0 + g1, (t0 + t1).cpu().numpy()
     ta = t_all.cpu().numpy()
     tn = t_again.cpu().numpy()

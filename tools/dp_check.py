@@ -1,5 +1,5 @@
-"""Data-parallel check on real GPUs (torchrun, one rank per GPU, NCCL): the bucketed gradient all-reduce underneath the backward
-pass, eager and with the step replayed as CUDA-graph segments.  Every rank: identical replicas, its own shard; after a step (eager, then graph replay) the all-reduced flat gradient
+"""Data-parallel check on real GPUs (torchrun, one rank per GPU, NCCL): the gradient all-reduce between the backward pass and Adam
+(default) and in buckets underneath the backward pass, eager and with the step replayed as CUDA-graph segments.  Every rank: identical replicas, its own shard; after a step (eager, then graph replay) the all-reduced flat gradient
 must be bit-identical on every rank and equal to the sum of the ranks' local gradients (computed by a second replica whose
 collective is the identity and summed with one plain all_reduce); weights stay identical across ranks over several steps.
 
@@ -35,16 +35,17 @@ def main():
     gen = torch.Generator().manual_seed(100 + rank)
     ok = True
 
-    def make(allreduce=None, use_graph=False):
+    def make(allreduce=None, use_graph=False, bucketed=False):
         net = create_hourglass_network(82, stacks).to(dev)
         net.load_state_dict(w2)
-        st = SelfSupTrainStep(net, hand, blob, B, V, Ns, S, lr=1e-4, world_size=world, use_graph=use_graph, allreduce=allreduce)
+        st = SelfSupTrainStep(net, hand, blob, B, V, Ns, S, lr=1e-4, world_size=world, use_graph=use_graph, allreduce=allreduce,
+                              bucketed=bucketed)
         return st
 
     real, cams, inv = data.synthetic_real_batch(hand, B, V, S, gen)
     poses = data.random_poses(Ns, gen)
-    for mode in ('eager', 'graph'):
-        a = make(use_graph=(mode == 'graph'))                 # the real thing: bucketed NCCL all-reduce
+    for mode in ('eager', 'graph', 'graph+buckets'):
+        a = make(use_graph=(mode != 'eager'), bucketed=mode.endswith('buckets'))      # the real thing: NCCL all-reduce(s)
         b = make(allreduce=lambda t: t, use_graph=False)      # same step, collective = identity -> the local gradient
         for st in (a, b):
             st.load_batch(real, cams, inv, poses)
@@ -75,7 +76,7 @@ def main():
                 print('%s step %d: reduced gradient identical on all ranks: %s; vs sum of local gradients l2 %.3e; weights identical: %s; '
                       'global loss %.4f' % (mode, it, same, err, same_w, terms['total']), flush=True)
             ok = ok and same and same_w and err < 0.25 and np.isfinite(terms['total'])
-        if mode == 'graph' and rank == 0:
+        if mode != 'eager' and rank == 0:
             print('launches per step', a.launches_per_step, flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
