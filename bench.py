@@ -482,7 +482,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--legs', type=int, default=1, help='0: skip the reference-GPU / drop-in / renderer / CPU legs (N=1 only)')
-    ap.add_argument('--real_aug', type=int, default=0, help='1: the scale augmentation of the real views inside the timed step')
+    ap.add_argument('--real_aug', type=int, default=1, help="the reference's scale augmentation of the real views inside the timed step (Engine's default: "
+                    'HeatmapEstimationNetwork(real_aug=True)); 0 = off')
     ap.add_argument('--bucketed', type=int, default=0, help='1: all-reduce the gradient in buckets underneath the backward pass instead of once after it (N > 1; measured slower)')
     ap.add_argument('--sample_poses', type=int, default=0, help='1: draw the synthetic poses on the device every step')
     args = ap.parse_args()

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden
+from conftest import golden, check_grads
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
@@ -62,27 +62,20 @@ def test_train_step_terms_and_gradients_vs_oracle(hand_model):
     terms = step.step(is_mv=True).cpu().numpy()
     assert np.isfinite(terms).all()
     batch.update(scales=step.scales.cpu(), rand_f=step.rand_f.cpu(), noise=step.noise.cpu(), eps=step.vae_eps.cpu())
-    sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
-    ref, grads, _ = ofs.train_step(sd, stacks, ofs.HandTables(hand_model), vae_sd, batch, S, apply_update=False, round_bf16=True)
+    out = {}
+    for mode in ('fp32', 'emul'):
+        sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+        out[mode] = ofs.train_step(sd, stacks, ofs.HandTables(hand_model), vae_sd, batch, S, apply_update=False, round_bf16=(mode == 'emul'))
+    ref, grads = out['emul'][0], out['fp32'][1]
     for k, v in zip(TERM_NAMES, terms):
         assert abs(v - ref[k]) <= 5e-2 * abs(ref[k]) + 1e-3, (k, float(v), ref[k])
     assert abs(terms[-1] - terms[:-1].sum()) <= 1e-5 * abs(terms[-1])                      # 'total' is the sum of the 8 terms
-    # parameter gradients (the flat buffer the all-reduce and Adam see) against the oracle's autograd
-    ours, theirs, per = [], [], []
-    for name, p in step.net.named_parameters():
-        g = step.net.grad_view(p).detach().float().cpu().reshape(-1)
-        r = grads[name].reshape(-1)
-        ours.append(g)
-        theirs.append(r)
-        per.append((float(r.norm()), float(g.norm()), name))
-    ours, theirs = torch.cat(ours), torch.cat(theirs)
-    cos = float(torch.dot(ours, theirs) / (ours.norm() * theirs.norm()))
-    ratio = float(ours.norm() / theirs.norm())
-    worst = max(abs(g - r) / r for r, g, _ in sorted(per, reverse=True)[:20])
-    print('gradient cosine %.4f  norm ratio %.4f  worst of the 20 largest parameters %.3f' % (cos, ratio, worst))
-    # random weights give flat heat-maps whose soft-argmax amplifies the bf16 rounding of the network (same effect as in
-    # test_gpu_modules.py): direction and size of the whole gradient are held tightly, single tensors loosely
-    assert cos > 0.95 and abs(ratio - 1) < 0.15 and worst < 0.5
+    # parameter gradients (the flat buffer the all-reduce and Adam see) against the fp32 oracle's autograd, held to what bf16
+    # activations allow: the error of torch evaluating the same graph with bf16 rounding at the kernels' materialisation points
+    # (random weights: flat heat-maps, the soft-argmax amplifies the rounding; the tight joint / term bounds are on trained weights,
+    # tests/test_gpu_trained.py)
+    ours = {name: step.net.grad_view(p).detach().float().cpu() for name, p in step.net.named_parameters()}
+    check_grads(ours, grads, out['emul'][1], 'fused step, deterministic random weights', cos_min=0.95)
     # the fused Adam on OUR gradient == torch.optim.Adam(lr, weight_decay=1e-5) on the same gradient (engine.py:95-97 of the reference)
     p_ref = flat0.clone().requires_grad_(True)
     p_ref.grad = step.net._flat_grad.clone()

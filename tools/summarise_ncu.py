@@ -72,12 +72,12 @@ def families(path, dst, note):
     names, vals = rows_of(path)
     out = {}
     for i, n in names.items():
-        tag = n.split('(')[0].strip()
+        tag = n.split('/')[0].strip()               # "<NVTX range = C-ABI call>/<kernel>"
         fam = FAMILY_OF_TAG.get(tag)
         if fam is None:
             continue
         d = out.setdefault(fam, dict(launches=0, dram_read_bytes=0.0, dram_write_bytes=0.0, total_us_under_ncu=0.0))
-        if vals[i].get('gpu__time_duration.sum', 0.0) < 3000.0 and tag in ('sh_mvproj_loss_fwdbwd',):
+        if tag == 'sh_mvproj_loss_fwdbwd' and 'mvproj_main_kernel' not in n:
             pass                                  # prep / finish kernels of the call: their bytes count, not their launch
         else:
             d['launches'] += 1
@@ -89,17 +89,6 @@ def families(path, dst, note):
         d['source'] = note
     json.dump(out, open(dst, 'w'), indent=1)
     print(json.dumps(out, indent=1))
-
-
-if __name__ == '__main__':
-    if sys.argv[1] == 'launches':
-        launches(*sys.argv[2:5])
-    elif sys.argv[1] == 'families':
-        families(*sys.argv[2:5])
-    elif sys.argv[1] == 'reps':
-        reps(sys.argv[2], [tuple(a.split('=', 1)) for a in sys.argv[3:]])
-    else:
-        traffic(*sys.argv[2:6])
 
 
 def reps(dst, pairs):
@@ -121,3 +110,14 @@ def reps(dst, pairs):
                 rec = dict(zip(hdr, r))
                 w.writerow([path.split('/')[-1], what] + [(rec.get(c, '')[:70] + (' ' + unit[c] if unit.get(c) and c != 'Kernel Name' else '')).strip()
                                                            for c in cols])
+
+
+if __name__ == '__main__':
+    if sys.argv[1] == 'launches':
+        launches(*sys.argv[2:5])
+    elif sys.argv[1] == 'families':
+        families(*sys.argv[2:5])
+    elif sys.argv[1] == 'reps':
+        reps(sys.argv[2], [tuple(a.split('=', 1)) for a in sys.argv[3:]])
+    else:
+        traffic(*sys.argv[2:6])
