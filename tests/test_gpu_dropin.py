@@ -100,6 +100,25 @@ def test_dropin_step_matches_stock_reference(tmp_path):
 
 @pytest.mark.gpu
 @needs_ref
+def test_baseline_size_step_matches_stock_reference():
+    """BASELINE config 4 at its REAL size -- B=64 tuples x 3 views + 64 synthetic poses, 128x128, 2 stacks, heat-map 32, scale
+    augmentation on -- through the unmodified reference on this GPU (eager PyTorch fp32, TF32 off; ~50 GB) and through the installed
+    modules, same seeds (torch's default initialisation of the 2-stack network): every loss term of the first step."""
+    out = {m: run('--mode', m, '--S', '128', '--stacks', '2', '--B', '64', '--Ns', '64', '--steps', '1', '--warmup', '1', '--seed', '0')
+           for m in ('stock', 'dropin')}
+    s, d = out['stock'], out['dropin']
+    print('stock  terms', s['terms'])
+    print('dropin terms', d['terms'])
+    assert s['B'] == d['B'] == 64 and s['images_per_step'] == 256, (s['B'], s['note'])          # no out-of-memory fallback happened
+    total = abs(s['terms']['loss'])
+    for k, v in s['terms'].items():
+        hinge = k in ('term.collision', 'term.bone_length')
+        tol = (0.1 * abs(v) + 2e-3 * total) if hinge else (5e-2 * abs(v) + 1e-6)
+        assert abs(d['terms'][k] - v) <= tol, (k, d['terms'][k], v)
+
+
+@pytest.mark.gpu
+@needs_ref
 def test_unmodified_engine_epoch_in_both_worlds():
     out = {m: run('--mode', m, '--engine', '1', '--B', '8', '--seed', '5') for m in ('stock', 'dropin')}
     s, d = out['stock'], out['dropin']

@@ -75,6 +75,37 @@ def test_trained_hourglass(S, stacks, hm):
     check_grads(ours, grads['fp32'], grads['emul'], 'trained hourglass %d' % S)
 
 
+def test_hourglass_config3_full_size(hand_model):
+    """BASELINE config 3 at its real size (hourglass 2 stacks, 128x128, batch 64, forward + backward) against the oracle run in fp32
+    on this GPU (torch, TF32 off): heat-maps within the bf16 contract, parameter gradients on the bf16 yardstick.  Inputs:
+    sphere-rendered hands; weights: the trained-weight recipe (peaked heat-maps)."""
+    from spherehand_b200 import data
+    from spherehand_b200.model import HandModel
+    N, S, stacks = 64, 128, 2
+    sd0 = weights(stacks)
+    hand = HandModel.from_arrays(hand_model, DEV)
+    real, _, _ = data.synthetic_real_batch(hand, N, 1, S, torch.Generator().manual_seed(5))
+    x = (real.reshape(N, S, S) * 0.01).contiguous()
+    net = create_hourglass_network(82, stacks).to(DEV)
+    net.load_state_dict(sd0)
+    outs, _ = net(x)
+    gs = [torch.from_numpy(oh.det_uniform(o.numel(), 400 + i).reshape(o.shape)).to(DEV) for i, o in enumerate(outs)]
+    sum((o * gg).sum() for o, gg in zip(outs, gs)).backward()
+    ours = {k: p.grad for k, p in net.named_parameters()}
+    grads, fwd = {}, {}
+    for mode in ('fp32', 'emul'):
+        sd = {k: v.to(DEV).clone().requires_grad_(True) for k, v in sd0.items()}
+        o2, _ = oh.hourglass_forward(x, sd, stacks, round_bf16=(mode == 'emul'))
+        sum((o * gg).sum() for o, gg in zip(o2, gs)).backward()
+        grads[mode] = {k: v.grad for k, v in sd.items()}
+        fwd[mode] = [o.detach() for o in o2]
+    for i, o in enumerate(outs):
+        e = (rel_err(o.detach().cpu(), fwd['fp32'][i].cpu()), l2(o.detach(), fwd['fp32'][i]))
+        print('config 3 (N=64, 128x128, 2 stacks) stack %d: heat-map max-norm err %.4f, l2 %.4f' % (i, *e))
+        assert e[0] < 2.5e-2 and e[1] < 1e-2
+    check_grads(ours, grads['fp32'], grads['emul'], 'hourglass config 3, full size')
+
+
 def joint_bounds(ours, ref, S, what):
     rng = float(ref.max() - ref.min())
     d = np.abs(np.asarray(ours, np.float64) - ref)
