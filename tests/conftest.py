@@ -59,7 +59,7 @@ def l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def check_grads(ours, ref, emul, what, cos_min=0.98):
+def check_grads(ours, ref, emul, what, cos_min=0.98, agg=1.25):
     """ours / ref / emul: dict name -> gradient.  The yardstick is the bf16 emulation's own error against the fp32 reference.  Two runs
     of the SAME step already differ by 6-12 % per tensor (tools/diag_noise.py: the order of the fp32 statistics atomics flips single
     bf16 roundings and the deep network amplifies them), so single tensors get a loose bound (2 x emulated + 5e-2) and the stable
@@ -79,8 +79,8 @@ def check_grads(ours, ref, emul, what, cos_min=0.98):
           '(emulated %.4f); worst vs yardstick: %s' % (what, cos, cos_e, l2(fo, fr), l2(fe, fr), float(np.median([r[2] for r in rows])),
                                                        float(np.median([r[3] for r in rows])), [(k, '%.3f' % a, '%.3f' % b) for _, k, a, b in rows[:3]]))
     assert rows[0][0] < 5e-2, rows[0]
-    assert l2(fo, fr) <= 1.25 * l2(fe, fr) + 1e-2
-    assert float(np.median([r[2] for r in rows])) <= 1.25 * float(np.median([r[3] for r in rows])) + 1e-2
+    assert l2(fo, fr) <= agg * l2(fe, fr) + 1e-2
+    assert float(np.median([r[2] for r in rows])) <= agg * float(np.median([r[3] for r in rows])) + 1e-2
     assert cos > cos_min and cos > cos_e - 0.01
 
 

@@ -75,7 +75,8 @@ def test_train_step_terms_and_gradients_vs_oracle(hand_model):
     # (random weights: flat heat-maps, the soft-argmax amplifies the rounding; the tight joint / term bounds are on trained weights,
     # tests/test_gpu_trained.py)
     ours = {name: step.net.grad_view(p).detach().float().cpu() for name, p in step.net.named_parameters()}
-    check_grads(ours, grads, out['emul'][1], 'fused step, deterministic random weights', cos_min=0.95)
+    # (random weights: two noise realisations of a 20 % effect, aggregates within 1.5 x; trained weights hold 1.25 x)
+    check_grads(ours, grads, out['emul'][1], 'fused step, deterministic random weights', cos_min=0.95, agg=1.5)
     # the fused Adam on OUR gradient == torch.optim.Adam(lr, weight_decay=1e-5) on the same gradient (engine.py:95-97 of the reference)
     p_ref = flat0.clone().requires_grad_(True)
     p_ref.grad = step.net._flat_grad.clone()
