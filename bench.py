@@ -152,6 +152,13 @@ def call_work(name, a):
         flops = 2.0 * px * a[7] * a[8] * a[10]
         byts = px * (2 * a[7] + (2 * a[12] if a[11] else 0) + (2 * a[8] if a[3] else 0) + (4 * a[8] if a[13] else 0))
         return flops, byts, 'conv3x3' if a[10] == 9 else 'conv1x1'
+    if name == 'sh_conv_fwd_gn':   # (x,gn_stats,gamma,beta,G,eps,w,bias,res,N,H,W,Cin,Cout,cout_pad,y,y_ld,y_nchw,stats,groups,stream)
+        px = float(a[9] * a[10] * a[11])
+        byts = px * (2 * a[12] + (2 * a[16] if a[15] else 0) + (2 * a[13] if a[8] else 0) + (4 * a[13] if a[17] else 0))
+        return 2.0 * px * a[12] * a[13], byts, 'conv1x1'
+    if name == 'sh_conv_wgrad_gn':  # (dy,x,gn_stats,gamma,beta,G,eps,N,H,W,x_C,Cin,dy_C,Cout,dw,stream)
+        px = float(a[7] * a[8] * a[9])
+        return 2.0 * px * a[11] * a[13], px * 2 * (a[10] + a[12]), 'wgrad1x1'
     if name == 'sh_conv_wgrad':    # (dy,x,N,H,W,x_C,Cin,dy_C,Cout,taps,dw,stream)
         px = float(a[2] * a[3] * a[4])
         return 2.0 * px * a[6] * a[8] * a[9], px * 2 * (a[5] + a[7]), 'wgrad3x3' if a[9] == 9 else 'wgrad1x1'

@@ -144,6 +144,15 @@ int sh_heatmap_render(const void* uvd, int B, int J, int hm, float sigma, float 
 int sh_conv_fwd(const void* x, const void* w, const void* bias, const void* residual, int N, int H, int W, int Cin,
                 int Cout, int cout_pad, int taps, void* y, int y_ld, void* y_nchw, void* stats, int groups,
                 void* stream);
+/* The same 1x1 convolution on a = relu(groupnorm(x)) with x the RAW GroupNorm input (gn_stats [N,gn_groups,2] = its per-(sample,
+ * group) sum / sum of squares, gn_gamma / gn_beta [Cin]): GroupNorm + ReLU (network/hourglass.py:26-36) are applied to every
+ * operand tile in shared memory between the TMA arrival and the MMA; bit-identical to sh_gn_relu_fwd followed by sh_conv_fwd.
+ * Images of >= 64 pixels.  sh_conv_wgrad_gn: the matching weight gradient (x_C == Cin). */
+int sh_conv_fwd_gn(const void* x, const void* gn_stats, const void* gn_gamma, const void* gn_beta, int gn_groups, float gn_eps,
+                   const void* w, const void* bias, const void* residual, int N, int H, int W, int Cin, int Cout, int cout_pad,
+                   void* y, int y_ld, void* y_nchw, void* stats, int groups, void* stream);
+int sh_conv_wgrad_gn(const void* dy, const void* x, const void* gn_stats, const void* gn_gamma, const void* gn_beta, int gn_groups,
+                     float gn_eps, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout, void* dw, void* stream);
 /* dw fp32 [Cout,Cin,k,k] (reference layout) += dY^T X (accumulated atomically: zero first).  dy bf16 [N,H,W,dy_C],
  * x bf16 [N,H,W,x_C]; x_C, dy_C multiples of 64; Cin <= x_C and Cout <= dy_C are the real channel counts. */
 int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout, int taps,

@@ -24,15 +24,18 @@
 //     HBM-bound 1x1 layers (ncu: the MMA and the TMA ring wait on it), and a warp cannot hide its own dependent-issue
 //     latencies; group (b, h) serves accumulator buffer b (alternate tiles) and the 64-channel chunks c = h, h+2, ...
 //     of it, 32 columns at a time (register budget of a 576-thread CTA), with its own staging slot.
-// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..17 = epilogue groups 0..3 (4 warps each, one TMEM lane quadrant per warp).
+// Warp roles (704 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..17 = epilogue groups 0..3 (4 warps each, one TMEM lane quadrant per warp), warps 18..21 = operand transform
+// (fused GroupNorm + ReLU of a 1x1 layer's input, applied to every A tile in shared memory between the TMA arrival and the MMA;
+// idle otherwise).
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int kBM = 128;           // pixels per tile = TMEM lanes
 constexpr int kBK = 64;            // channels per k-block = one 128-byte swizzle row
-constexpr int kThreads = 576;
+constexpr int kThreads = 576;       // producer + MMA + 16 epilogue warps
+constexpr int kThreadsXf = 704;     // + 4 operand-transform warps (fused GroupNorm of a 1x1 layer's input): the non-halo build
 constexpr int kMaxStages = 8;
 constexpr int kGroups = 4;         // epilogue warp-groups, one 16 KB staging slot each
 constexpr int kABytes = kBM * kBK * 2;          // 16 KB
@@ -62,12 +65,14 @@ struct ConvGeom {
     int b_resident;                // weights loaded once per CTA
     int has_res;                   // residual tile fetched by TMA
     int nchunks;                   // 64-channel output chunks the epilogue processes
+    int fuse_gn;                   // A tiles are x; the MMA multiplies relu(groupnorm(x)) (1x1 layers, <= 2 images per tile)
 };
 
 struct ConvPtrs {
     const float* bias;             // [cout] or null
     float* y_nchw;                 // [N,cout,H,W] fp32 or null
     float* stats;                  // [N,groups,2] fp32 (sum, sum of squares), accumulated atomically
+    GnOperand gn;                  // fused GroupNorm of the INPUT (groups == 0: none)
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
@@ -152,7 +157,7 @@ __device__ __forceinline__ void row_stats(const uint32_t (&packed)[NW], bool row
 }
 
 template <int BN, bool HALO>
-__global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(HALO ? kThreads : kThreadsXf, 1) conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmRes,
                                                                const __grid_constant__ CUtensorMap tmOut,
@@ -177,7 +182,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
     uint64_t* acc_empty = acc_full + 4;                         // [4]
     uint64_t* halo_full = acc_empty + 4;                        // [kHaloSlots]
     uint64_t* halo_empty = halo_full + kHaloSlots;              // [kHaloSlots]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(halo_empty + kHaloSlots);
+    uint64_t* xf_bar = halo_empty + kHaloSlots;                 // [kMaxStages]: the A tile of the stage has been transformed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf_bar + kMaxStages);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);    // [256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -192,12 +198,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
         // a buffer is drained by one group (single-chunk layers) or by the two groups that split its chunks
         for (int b = 0; b < 4; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], g.nchunks >= 2 ? 256 : 128); }
         for (int s = 0; s < kHaloSlots; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], 1); }
+        for (int s = 0; s < kMaxStages; ++s) mbar_init(&xf_bar[s], 32);
         mbar_fence_init();
     }
-    for (int i = threadIdx.x; i < 256; i += kThreads) s_bias[i] = (p.bias && i < g.cout) ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = (p.bias && i < g.cout) ? p.bias[i] : 0.f;
     if (g.has_res) {
         // I[n][k] = (n == k), K-major rows of 128 B with the 128-byte swizzle: 16-byte chunk j of row n sits at chunk j ^ (n & 7)
-        for (int i = threadIdx.x; i < kIdentBytes / 16; i += kThreads) {
+        for (int i = threadIdx.x; i < kIdentBytes / 16; i += blockDim.x) {
             const int n = i >> 3, j = i & 7;                    // row, logical chunk (channels 8j .. 8j+7)
             uint32_t w4[4] = {0u, 0u, 0u, 0u};
             if ((n >> 3) == j) w4[(n & 7) >> 1] = (n & 1) ? 0x3f800000u : 0x00003f80u;      // bf16 1.0 at element n % 8
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
                 for (int k = 0; k < num_k; ++k, ++it) {
                     const int s = it % g.stages, ph = (it / g.stages) & 1;
-                    mbar_wait(&full_bar[s], ph);
+                    mbar_wait(g.fuse_gn ? &xf_bar[s] : &full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(s_pipe + s * stage_bytes);
                     const uint32_t b_addr = g.b_resident ? smem_u32(s_bres + k * kBBytes) : a_addr + kABytes;
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
                     const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(s_ident));
                     for (int c = 0; c < g.nchunks; ++c, ++it) {
                         const int s = it % g.stages, ph = (it / g.stages) & 1;
-                        mbar_wait(&full_bar[s], ph);
+                        mbar_wait(g.fuse_gn ? &xf_bar[s] : &full_bar[s], ph);
                         tc_fence_after();
                         const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(s_pipe + s * stage_bytes));
 #pragma unroll
@@ -361,6 +368,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
                     }
                 }
                 umma_commit(&acc_full[buf]);                    // accumulator complete
+            }
+        }
+    } else if (warp >= 18) {
+        // ===================== operand transform: A := relu(groupnorm(x)) in shared memory =====================
+        if (!HALO && g.fuse_gn) {
+            // one warp per pipeline stage (4 stages in flight): the transform of a tile is a chain of dependent latencies (scale /
+            // shift loads -> barrier wait -> shared-memory round trip), so four tiles must overlap to keep up with the TMA ring
+            // A stage always belongs to the same warp, so a warp meets the phases of its barriers in order.
+            const int xw = warp - 18;                           // this warp owns the stages s % 4 == xw
+            const int j = lane & 7, r0 = lane >> 3;             // 16-byte chunk of the 128-byte rows; rows r0, r0+4, ..., r0+124
+            int it = 0;
+            for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+                const TileCoord t = tile_coord(g, tile);
+                const int nA = min(t.n0, g.N - 1), nB = min(t.n0 + g.bn - 1, g.N - 1);   // rows 0..63 / 64..127 (bn <= 2)
+                for (int k = 0; k < num_k; ++k, ++it) {         // taps == 1: k is the 64-channel block
+                    const int s = it % g.stages, ph = (it / g.stages) & 1;
+                    if ((s & 3) != xw) continue;
+                    float ka[8], kb[8];
+                    gn_scale_shift(p.gn, nA, k * kBK + j * 8, ka, kb);                   // (global loads: issued before the wait)
+                    mbar_wait(&full_bar[s], ph);
+                    const uint32_t tileA = smem_u32(s_pipe + s * stage_bytes);
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {                                        // rows 0..63 (image nA), 64..127 (image nB)
+                        if (h == 1 && nB != nA) gn_scale_shift(p.gn, nB, k * kBK + j * 8, ka, kb);
+                        gn_xform_rows<16>(tileA + h * 64 * 128, r0, j, ka, kb);
+                    }
+                    fence_async_smem();                         // generic-proxy writes -> visible to tcgen05.mma
+                    mbar_arrive(&xf_bar[s]);
+                }
+                if (g.has_res) {                                // the residual tiles ride the same ring untransformed
+                    for (int c = 0; c < g.nchunks; ++c, ++it) {
+                        const int s = it % g.stages, ph = (it / g.stages) & 1;
+                        if ((s & 3) != xw) continue;
+                        mbar_wait(&full_bar[s], ph);
+                        mbar_arrive(&xf_bar[s]);
+                    }
+                }
             }
         }
     } else {
@@ -387,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fwd_kernel(const __grid_cons
             const bool row_ok = n < g.N;
             const int tl = buf + 2 * lt;                        // local tile index; its accumulator and barrier phase
             const int abuf = tl & (NACC - 1);
-            mbar_wait(&acc_full[abuf], (uint32_t)((tl / NACC) & 1));
+            mbar_wait_polite(&acc_full[abuf], (uint32_t)((tl / NACC) & 1));
             tc_fence_after();
             for (int c = half; c < g.nchunks; c += 2) {
                 const int cg = c * 64;                          // first channel of this chunk
@@ -481,7 +525,7 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
         SH_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr = true;
     }
-    conv_fwd_kernel<BN, HALO><<<grid, kThreads, smem, st>>>(tmA, tmB, tmRes, tmOut, g, p);
+    conv_fwd_kernel<BN, HALO><<<grid, HALO ? kThreads : kThreadsXf, smem, st>>>(tmA, tmB, tmRes, tmOut, g, p);
     SH_CHECK_LAUNCH("conv_fwd_kernel");
     return SH_OK;
 }
@@ -494,9 +538,9 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 //   residual bf16 [N,H,W,Cout] or null (Cout % 8 == 0)
 //   y        bf16 [N,H,W,y_ld] or null; y_nchw fp32 [N,Cout,H,W] or null; stats fp32 [N,groups,2] (accumulated) or null
 // The data-gradient is the same call on dY with flipped/transposed weights.
-SH_EXPORT int sh_conv_fwd(const void* x, const void* w, const void* bias, const void* residual, int N, int H, int W,
-                           int Cin, int Cout, int cout_pad, int taps, void* y, int y_ld, void* y_nchw, void* stats,
-                           int groups, void* stream) {
+static int conv_fwd_impl(const void* x, const void* w, const void* bias, const void* residual, int N, int H, int W,
+                         int Cin, int Cout, int cout_pad, int taps, void* y, int y_ld, void* y_nchw, void* stats,
+                         int groups, const GnOperand& gn, void* stream) {
     SH_REQUIRE(x && w && (y || y_nchw), "sh_conv_fwd: null pointer");
     SH_REQUIRE(taps == 1 || taps == 9, "sh_conv_fwd: taps must be 1 or 9");
     SH_REQUIRE(N >= 1 && is_pow2(H) && is_pow2(W) && H >= 4 && W >= 4, "sh_conv_fwd: H, W must be powers of two >= 4");
@@ -523,6 +567,13 @@ SH_EXPORT int sh_conv_fwd(const void* x, const void* w, const void* bias, const 
     g.y_ld = y ? y_ld : 0;
     g.groups = stats ? groups : 0;
     g.has_res = residual ? 1 : 0;
+    g.fuse_gn = gn.groups > 0 ? 1 : 0;
+    if (g.fuse_gn) {
+        SH_REQUIRE(taps == 1 && g.bn <= 2, "sh_conv_fwd_gn: the fused input GroupNorm needs a 1x1 layer on images of >= 64 pixels");
+        SH_REQUIRE(gn.stats && gn.gamma && gn.beta && Cin % gn.groups == 0 && (gn.cpg == 4 || gn.cpg == 8 || gn.cpg == 16) &&
+                   (((uintptr_t)gn.gamma | (uintptr_t)gn.beta) & 15) == 0 && ((uintptr_t)gn.stats & 7) == 0,
+                   "sh_conv_fwd_gn: bad GroupNorm operand (4, 8 or 16 channels per group; 16-byte aligned gamma / beta)");
+    }
     const int top = (y && y_ld > Cout) ? y_ld : Cout;
     g.nchunks = (top + 63) / 64;
     // shared-memory plan: one 16 KB staging slot per epilogue group, resident weights if they fit next to >= 2 A stages
@@ -552,7 +603,7 @@ SH_EXPORT int sh_conv_fwd(const void* x, const void* w, const void* bias, const 
         }
     }
     SH_REQUIRE(g.stages >= 2, "sh_conv_fwd: shared-memory plan failed");
-    ConvPtrs p{(const float*)bias, (float*)y_nchw, (float*)stats};
+    ConvPtrs p{(const float*)bias, (float*)y_nchw, (float*)stats, gn};
     CUtensorMap tmA, tmB, tmRes, tmOut;
     int rc = halo ? make_act_tmap(&tmA, x, N, H, W, Cin, kHaloW, kHaloH, 1) : make_act_tmap(&tmA, x, N, H, W, Cin, g.bw, g.bh, g.bn);
     if (rc) return rc;
@@ -574,4 +625,24 @@ SH_EXPORT int sh_conv_fwd(const void* x, const void* w, const void* bias, const 
     if (cout_pad == 256) return launch_conv<256, false>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
     if (cout_pad == 128) return launch_conv<128, false>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
     return launch_conv<64, false>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+}
+
+SH_EXPORT int sh_conv_fwd(const void* x, const void* w, const void* bias, const void* residual, int N, int H, int W,
+                           int Cin, int Cout, int cout_pad, int taps, void* y, int y_ld, void* y_nchw, void* stats,
+                           int groups, void* stream) {
+    GnOperand none{};
+    return conv_fwd_impl(x, w, bias, residual, N, H, W, Cin, Cout, cout_pad, taps, y, y_ld, y_nchw, stats, groups, none, stream);
+}
+
+// The same 1x1 convolution on a = relu(groupnorm(x)): x is the RAW input of the GroupNorm (gn_stats [N,gn_groups,2] = its per-
+// (sample, group) sum / sum of squares, gn_gamma / gn_beta [Cin]); the normalisation + ReLU is applied to every operand tile in
+// shared memory between the TMA arrival and the MMA, so neither the gn_relu_fwd pass nor the tensor a exists.  Bit-identical to
+// sh_gn_relu_fwd followed by sh_conv_fwd.  Needs taps == 1 and images of >= 64 pixels.
+SH_EXPORT int sh_conv_fwd_gn(const void* x, const void* gn_stats, const void* gn_gamma, const void* gn_beta, int gn_groups, float gn_eps,
+                              const void* w, const void* bias, const void* residual, int N, int H, int W, int Cin, int Cout,
+                              int cout_pad, void* y, int y_ld, void* y_nchw, void* stats, int groups, void* stream) {
+    SH_REQUIRE(gn_groups >= 1 && Cin % gn_groups == 0, "sh_conv_fwd_gn: bad gn_groups");
+    GnOperand gn{(const float*)gn_stats, (const float*)gn_gamma, (const float*)gn_beta, gn_groups, Cin / gn_groups,
+                 1.f / ((float)(H * W) * (float)(Cin / gn_groups)), gn_eps};
+    return conv_fwd_impl(x, w, bias, residual, N, H, W, Cin, Cout, cout_pad, 1, y, y_ld, y_nchw, stats, groups, gn, stream);
 }

@@ -218,6 +218,8 @@ struct Wgrad1Geom {
     int cin_pad;                   // N of the MMA (64, 128 or 256)
     int co_tiles;                  // 1 or 2 accumulators of 128 rows
     int stages, stage_bytes;
+    int fuse_gn;                   // the X tiles are x; the MMA multiplies relu(groupnorm(x)) (one image per pixel tile)
+    GnOperand gn;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -235,7 +237,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad1x1_kernel(const __grid_cons
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + g.stages * g.stage_bytes);
     uint64_t* empty_bar = full_bar + kW1MaxStages;
     uint64_t* accum_bar = empty_bar + kW1MaxStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* xf_bar = accum_bar + 1;                        // [kW1MaxStages]: the X chunks of the stage have been transformed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf_bar + kW1MaxStages);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (g.total_tiles + gridDim.x - 1) / gridDim.x;
     const int tile_begin = blockIdx.x * per;
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad1x1_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmDY);
         tma_prefetch_desc(&tmX);
-        for (int s = 0; s < kW1MaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kW1MaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&xf_bar[s], 32); }
         mbar_init(accum_bar, 1);
         mbar_fence_init();
     }
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad1x1_kernel(const __grid_cons
             const uint32_t idesc = umma_idesc_bf16(128, g.cin_pad, 1, 1);
             for (int k = 0; k < num_k; ++k) {
                 const int s = k % g.stages, it = k / g.stages;
-                mbar_wait(&full_bar[s], it & 1);
+                mbar_wait(g.fuse_gn ? &xf_bar[s] : &full_bar[s], it & 1);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * g.stage_bytes);
                 const uint32_t b_addr = a_addr + a_bytes;
@@ -297,6 +300,29 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad1x1_kernel(const __grid_cons
             umma_commit(accum_bar);
         }
     } else {
+        if (g.fuse_gn) {
+            // the four epilogue warps are idle until the accumulator is complete: they apply GroupNorm + ReLU to the X chunks of
+            // every stage in shared memory (X in HBM is the raw GroupNorm input; its normalised form is never materialised)
+            // One warp per stage, four stages in flight (the chain scale / shift loads -> wait -> shared-memory round trip is latency).
+            // A stage always belongs to the same warp, so a warp meets the phases of its barriers in order.
+            const int xw = warp - 2;                            // this warp owns the stages s % 4 == xw
+            const int j = lane & 7, r0 = lane >> 3;             // 16-byte chunk of the 128-byte rows; rows r0, r0+4, ..., r0+60
+            const int tiles_per_img = g.tiles_w * g.tiles_h;    // bn == 1
+            for (int k = 0; k < num_k; ++k) {
+                const int s = k % g.stages, it = k / g.stages;
+                if ((s & 3) != xw) continue;
+                const int n = min((tile_begin + k) / tiles_per_img, g.N - 1);
+                uint8_t* b_dst = smem + s * g.stage_bytes + a_bytes;
+                for (int c = 0; c < g.cin_pad / 64; ++c) {
+                    float ka[8], kb[8];
+                    gn_scale_shift(g.gn, n, c * 64 + j * 8, ka, kb);          // (global loads: issued before the wait)
+                    if (c == 0) mbar_wait(&full_bar[s], it & 1);
+                    gn_xform_rows<kWPix / 4>(smem_u32(b_dst + c * kWPix * 128), r0, j, ka, kb);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&xf_bar[s]);
+            }
+        }
         const int quad = warp & 3;
         mbar_wait(accum_bar, 0);
         tc_fence_after();
@@ -537,8 +563,8 @@ static int launch_wgrad_generic(const void* dy, const void* x, int N, int H, int
 // Weight gradient: dw fp32 [Cout, Cin, k, k] (the reference layout) += dY^T X_shifted, accumulated atomically (zero it
 // first).  dy bf16 [N,H,W,dy_C], x bf16 [N,H,W,x_C]; Cout <= dy_C, Cin <= x_C are the real channel counts; channels
 // beyond dy_C / x_C needed to fill the 128-wide MMA tile are supplied as zeros by TMA's out-of-bounds fill.
-SH_EXPORT int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout, int taps,
-                            void* dw, void* stream) {
+static int conv_wgrad_impl(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout, int taps,
+                           void* dw, const GnOperand& gn, void* stream) {
     SH_REQUIRE(dy && x && dw, "sh_conv_wgrad: null pointer");
     SH_REQUIRE(taps == 1 || taps == 9, "sh_conv_wgrad: taps must be 1 or 9");
     SH_REQUIRE(N >= 1 && is_pow2(H) && is_pow2(W) && H >= 4 && W >= 4, "sh_conv_wgrad: H, W must be powers of two >= 4");
@@ -556,6 +582,14 @@ SH_EXPORT int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, 
         g1.cin = Cin; g1.cout = Cout;
         g1.cin_pad = x_C;
         g1.co_tiles = (dy_C + 127) / 128;
+        g1.fuse_gn = gn.groups > 0 ? 1 : 0;
+        g1.gn = gn;
+        if (g1.fuse_gn) {
+            SH_REQUIRE(g1.bn == 1, "sh_conv_wgrad_gn: the fused input GroupNorm needs images of >= 64 pixels");
+            SH_REQUIRE(gn.stats && gn.gamma && gn.beta && x_C % gn.groups == 0 && (gn.cpg == 4 || gn.cpg == 8 || gn.cpg == 16) &&
+                       (((uintptr_t)gn.gamma | (uintptr_t)gn.beta) & 15) == 0 && ((uintptr_t)gn.stats & 7) == 0,
+                       "sh_conv_wgrad_gn: bad GroupNorm operand (4, 8 or 16 channels per group; 16-byte aligned gamma / beta)");
+        }
         g1.stage_bytes = (g1.co_tiles * 2 + g1.cin_pad / 64) * kWPix * 128;
         g1.stages = (kSmemMax - 2048) / g1.stage_bytes;
         if (g1.stages > kW1MaxStages) g1.stages = kW1MaxStages;
@@ -577,7 +611,24 @@ SH_EXPORT int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, 
         SH_CHECK_LAUNCH("wgrad1x1_kernel");
         return SH_OK;
     }
+    SH_REQUIRE(gn.groups == 0, "sh_conv_wgrad_gn: only 1x1 layers with <= 256 channels take a fused input GroupNorm");
     return launch_wgrad_generic(dy, x, N, H, W, x_C, Cin, dy_C, Cout, taps, dw, 0, st);
+}
+
+SH_EXPORT int sh_conv_wgrad(const void* dy, const void* x, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout, int taps,
+                            void* dw, void* stream) {
+    GnOperand none{};
+    return conv_wgrad_impl(dy, x, N, H, W, x_C, Cin, dy_C, Cout, taps, dw, none, stream);
+}
+
+// The 1x1 weight gradient against a = relu(groupnorm(x)) where only the raw x exists in HBM (see sh_conv_fwd_gn): the X tiles are
+// normalised in shared memory by the warps that otherwise wait for the accumulator.  x_C == Cin (the GroupNorm's channel count).
+SH_EXPORT int sh_conv_wgrad_gn(const void* dy, const void* x, const void* gn_stats, const void* gn_gamma, const void* gn_beta, int gn_groups,
+                               float gn_eps, int N, int H, int W, int x_C, int Cin, int dy_C, int Cout, void* dw, void* stream) {
+    SH_REQUIRE(gn_groups >= 1 && x_C % gn_groups == 0 && x_C == Cin, "sh_conv_wgrad_gn: bad gn_groups / channel count");
+    GnOperand gn{(const float*)gn_stats, (const float*)gn_gamma, (const float*)gn_beta, gn_groups, x_C / gn_groups,
+                 1.f / ((float)(H * W) * (float)(x_C / gn_groups)), gn_eps};
+    return conv_wgrad_impl(dy, x, N, H, W, x_C, Cin, dy_C, Cout, 1, dw, gn, stream);
 }
 
 // 3x3 weight gradient into a [9][Cout][Cin] fp32 scratch (accumulated: zero it once per step).  W >= 16: the kernel-row kernel;

@@ -40,6 +40,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// The same wait for warps whose wake-up latency does not matter (a whole epilogue group waiting microseconds for its accumulator):
+// the bare try_wait loop above re-issues every few cycles, and 16 such warps take most of the issue slots of the 4 schedulers away from
+// the warps that have arithmetic to do (ncu: 70 % of a 1x1 layer's executed instructions were this loop).  Here the thread is
+// suspended by the hardware for up to the hinted time, then backs off with nanosleep.
+__device__ __forceinline__ void mbar_wait_polite(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra D_%=;\n\t"
+        "nanosleep.u32 64;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(2000u) : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -89,6 +104,70 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- GroupNorm + ReLU applied to an operand tile IN shared memory (between the TMA arrival and the MMA): the tile a convolution
+// (or its weight gradient) reads is x, and what it must multiply is a = relu(groupnorm(x)) -- this removes the separate
+// gn_relu_fwd pass (read x, write a) and the tensor a itself.  Tile layout: rows of 128 B (one pixel's 64 channels), 128-byte
+// swizzle (16-byte chunk j of row r sits at chunk j ^ (r & 7); the tile base is 1024-byte aligned).  A thread owns chunk j
+// (channels c0 .. c0+7 of the 64-channel block) and walks rows, so its 8 scale / shift pairs are loop-invariant.
+struct GnOperand {
+    const float* stats;      // [N, groups, 2] (sum, sum of squares) of x, written by whichever kernel produced x
+    const float* gamma;      // [C]
+    const float* beta;       // [C]
+    int groups;              // 0 = no fused GroupNorm
+    int cpg;                 // channels per group (4, 8 or 16)
+    float cnt_inv;           // 1 / (H * W * cpg)
+    float eps;
+};
+// y = x * ka + kb with ka = rstd * gamma, kb = beta - mean * ka: the same expressions, in the same order, as gn_relu_fwd_kernel
+__device__ __forceinline__ void gn_scale_shift(const GnOperand& q, int n, int c0, float (&ka)[8], float (&kb)[8]) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(q.gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(q.gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(q.beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(q.beta + c0 + 4));
+    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const int sh = 31 - __clz(q.cpg);                                         // cpg is a power of two
+    const int gi0 = c0 >> sh, gi1 = (c0 + 7) >> sh;                           // 8 channels span one group (cpg >= 8) or two (cpg == 4)
+    const float2 s0 = __ldg(reinterpret_cast<const float2*>(q.stats + ((size_t)n * q.groups + gi0) * 2));
+    const float2 s1 = __ldg(reinterpret_cast<const float2*>(q.stats + ((size_t)n * q.groups + gi1) * 2));
+    const float m0 = s0.x * q.cnt_inv, m1 = s1.x * q.cnt_inv;
+    const float r0 = rsqrtf(fmaxf(s0.y * q.cnt_inv - m0 * m0, 0.f) + q.eps), r1 = rsqrtf(fmaxf(s1.y * q.cnt_inv - m1 * m1, 0.f) + q.eps);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const bool hi = ((c0 + e) >> sh) != gi0;
+        const float mu = hi ? m1 : m0, rs = hi ? r1 : r0;
+        ka[e] = rs * ga[e];
+        kb[e] = fmaf(-mu, ka[e], be[e]);
+    }
+}
+// NR rows r0, r0+4, r0+8, ... (r0 < 4) of chunk j of the tile at shared address `tile`: relu(bf16(x * ka + kb)), in place.  Explicit
+// shared-space 128-bit accesses, four rows in flight (the loads of a batch are issued before its arithmetic: the loop is otherwise a
+// chain of shared-memory round trips), the ReLU folded into the bf16 conversion (round, then clamp == clamp, then round).
+template <int NR>
+__device__ __forceinline__ void gn_xform_rows(uint32_t tile, int r0, int j, const float (&ka)[8], const float (&kb)[8]) {
+    static_assert(NR % 4 == 0, "rows are processed four at a time");
+    const uint32_t a_even = tile + (uint32_t)(r0 * 128 + ((j ^ r0) << 4));                 // rows r0 + 8m:     row & 7 == r0
+    const uint32_t a_odd = tile + (uint32_t)((r0 + 4) * 128 + ((j ^ (r0 + 4)) << 4));      // rows r0 + 4 + 8m: row & 7 == r0 + 4
+#pragma unroll 1
+    for (int i = 0; i < NR; i += 4) {                    // (rolled: the unrolled form thrashes the instruction cache between roles)
+        uint32_t v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t addr = ((u & 1) ? a_odd : a_even) + (uint32_t)(((i + u) >> 1) * 1024);
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]) : "r"(addr) : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 y = __ffma2_rn(make_float2(__uint_as_float(v[u][e] << 16), __uint_as_float(v[u][e] & 0xffff0000u)),
+                                            make_float2(ka[2 * e], ka[2 * e + 1]), make_float2(kb[2 * e], kb[2 * e + 1]));
+                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(v[u][e]) : "f"(y.y), "f"(y.x));
+            }
+            const uint32_t addr = ((u & 1) ? a_odd : a_even) + (uint32_t)(((i + u) >> 1) * 1024);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[u][0]), "r"(v[u][1]), "r"(v[u][2]), "r"(v[u][3]) : "memory");
+        }
+    }
+}
 
 // ---- descriptors (bit layouts: PTX ISA "tcgen05 matrix/instruction descriptor"; cross-checked against
 //      cute/arch/mma_sm100_desc.hpp in the vendored CUTLASS tree)

@@ -11,12 +11,17 @@ fp32 GroupNorm statistics.  Precision contract: bf16 operands => heat-maps withi
 
 There is no CPU path: calling forward on CPU tensors raises.
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import ops
 
 BF16 = torch.bfloat16
+# GroupNorm + ReLU in front of a bottleneck's 1x1 layers is applied inside the convolution / weight-gradient kernels
+# (sh_conv_fwd_gn / sh_conv_wgrad_gn) instead of by a separate sh_gn_relu_fwd pass.  SH_FUSE_GN=0 keeps the separate pass.
+FUSE_GN = os.environ.get('SH_FUSE_GN', '1') != '0'
 
 
 def _ceil(x, m):
@@ -320,17 +325,20 @@ class _Run:
         return self.net._wcache[id(conv)]
 
     # -------------------------------------------------------------- layers
-    def conv(self, conv, a, a_C, out, residual=None, y_nchw=None, want_stats=True):
-        """out = conv(a) + bias (+ residual).  a: bf16 buffer [N,H,W,a_C]; out: _Tensor (or None with y_nchw)."""
+    def conv(self, conv, a, a_C, out, residual=None, y_nchw=None, want_stats=True, gn=None):
+        """out = conv(a) + bias (+ residual).  a: bf16 buffer [N,H,W,a_C]; out: _Tensor (or None with y_nchw).
+        gn = (x, GroupNorm module): `a` is x.buf, the RAW GroupNorm input, and relu(groupnorm(.)) is applied to the operand tiles
+        inside the convolution and inside its weight gradient (no normalised copy of x is ever written)."""
         net, N = self.net, self.N
         Cout, Cin, k, _ = conv.weight.shape
         taps = k * k
         wf, wb, cout_pad, cin_pad, b_rows, b_cols = self.packed(conv)
         H, W = (out.H, out.W) if out is not None else y_nchw.shape[-2:]
         assert cin_pad == a_C, (cin_pad, a_C)
+        gn_op = (gn[0].stats, gn[1].weight.data, gn[1].bias.data, 16, 1e-5) if gn is not None else None
         ops.conv_fwd(a, wf, conv.bias.data, N, H, W, a_C, Cout, cout_pad, taps,
                      y=out.buf if out is not None else None, y_ld=out.C if out is not None else 0, y_nchw=y_nchw,
-                     residual=residual, stats=out.stats if (out is not None and want_stats) else None, groups=16)
+                     residual=residual, stats=out.stats if (out is not None and want_stats) else None, groups=16, gn=gn_op)
 
         def bwd(dout, dout_C, need_dx=True, dx_addend=None):
             """dout: bf16 [N,H,W,dout_C] gradient of the conv output -> returns bf16 gradient w.r.t. `a`."""
@@ -338,7 +346,7 @@ class _Run:
                 off3, n3 = net._wg3[id(conv)]
                 ops.conv_wgrad3x3(dout, a, N, H, W, a_C, Cin, dout_C, Cout, net._wg3_scratch[off3:off3 + n3])
             else:
-                ops.conv_wgrad(dout, a, N, H, W, a_C, Cin, dout_C, Cout, taps, net.grad_view(conv.weight))
+                ops.conv_wgrad(dout, a, N, H, W, a_C, Cin, dout_C, Cout, taps, net.grad_view(conv.weight), gn=gn_op)
             if not need_dx:
                 return None
             dx = torch.empty((N, H, W, a_C), device=self.dev, dtype=BF16)
@@ -349,12 +357,16 @@ class _Run:
             return dx
         return bwd
 
-    def gn_relu(self, x, gn, G=16, out_stats=False, G_out=16):
-        """a = relu(groupnorm(x)); returns (a buffer, [stats of a], backward closure)."""
+    def gn_relu(self, x, gn, G=16, out_stats=False, G_out=16, fused=False):
+        """a = relu(groupnorm(x)); returns (a buffer, [stats of a], backward closure).  fused: the consumer applies the
+        normalisation itself (conv(..., gn=)); only the backward closure is built and `a` is x.buf."""
         N = self.N
-        a = torch.empty_like(x.buf)
         st = self.new_stats() if out_stats else None
-        ops.gn_relu_fwd(x.buf, x.stats, gn.weight.data, gn.bias.data, N, x.H * x.W, x.C, G, a, st, G_out)
+        if fused:
+            a = x.buf
+        else:
+            a = torch.empty_like(x.buf)
+            ops.gn_relu_fwd(x.buf, x.stats, gn.weight.data, gn.bias.data, N, x.H * x.W, x.C, G, a, st, G_out)
         net = self.net
 
         # scratch of this layer's backward: a slice of ONE arena zeroed once per backward pass (one fill instead of a memset
@@ -377,13 +389,16 @@ class _Run:
         net, N = self.net, self.N
         planes = blk.conv1.weight.shape[0]
         H, W = x.H, x.W
-        a1, _, gn1_b = self.gn_relu(x, blk.bn1)
+        # GroupNorm + ReLU in front of the two 1x1 layers runs inside them (images of >= 64 pixels)
+        fuse = FUSE_GN and H * W >= 64
+        fuse3 = fuse and planes > 64        # (64 -> 128 with the residual at 64x64 measures slower fused: tools/bench_fused_gn.py)
+        a1, _, gn1_b = self.gn_relu(x, blk.bn1, fused=fuse)
         t1 = self.act(H, W, planes)
-        c1_b = self.conv(blk.conv1, a1, x.C, t1)
+        c1_b = self.conv(blk.conv1, a1, x.C, t1, gn=(x, blk.bn1) if fuse else None)
         a2, _, gn2_b = self.gn_relu(t1, blk.bn2)
         t2 = self.act(H, W, planes)
         c2_b = self.conv(blk.conv2, a2, planes, t2)
-        a3, _, gn3_b = self.gn_relu(t2, blk.bn3)
+        a3, _, gn3_b = self.gn_relu(t2, blk.bn3, fused=fuse3)
         out = self.act(H, W, planes * 2)
         if blk.downsample is not None:
             res = self.act(H, W, planes * 2, stats=False)
@@ -391,7 +406,7 @@ class _Run:
             res_buf = res.buf
         else:
             d_b, res_buf = None, x.buf
-        c3_b = self.conv(blk.conv3, a3, planes, out, residual=res_buf)
+        c3_b = self.conv(blk.conv3, a3, planes, out, residual=res_buf, gn=(t2, blk.bn3) if fuse3 else None)
         # bias gradients of conv3 (and of the downsample conv, which sees the same output gradient) = colsum(dL/dout)
         out.bias_grads = [net.grad_view(blk.conv3.bias)] + ([net.grad_view(blk.downsample[0].bias)] if d_b is not None else [])
 

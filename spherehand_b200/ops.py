@@ -220,13 +220,31 @@ def heatmap_render(uvd, hm, sigma=1.0, uv_scale=1.0, depth_scale=1.0, cam=None):
 
 
 def conv_fwd(x, w, bias, N, H, W, Cin, Cout, cout_pad, taps, y=None, y_ld=0, y_nchw=None, residual=None, stats=None,
-             groups=0):
+             groups=0, gn=None):
+    """gn = (stats [N,G,2], gamma, beta, G, eps): x is the RAW GroupNorm input and relu(groupnorm(x)) is formed in shared memory
+    (1x1 layers, images of >= 64 pixels)."""
+    if gn is not None:
+        gst, gamma, beta, G, eps = gn
+        if taps != 1:
+            raise RuntimeError('conv_fwd: only 1x1 layers take a fused input GroupNorm')
+        _call('sh_conv_fwd_gn', _chk(x, BF16, 'x'), _chk(gst, name='gn_stats'), _chk(gamma, name='gamma'), _chk(beta, name='beta'), G, eps,
+              _chk(w, BF16, 'w'), _opt(bias, name='bias'), _opt(residual, BF16, 'residual'), N, H, W, Cin, Cout, cout_pad,
+              _opt(y, BF16, 'y'), y_ld, _opt(y_nchw, name='y_nchw'), _opt(stats, name='stats'), groups, _stream())
+        return
     _call('sh_conv_fwd', _chk(x, BF16, 'x'), _chk(w, BF16, 'w'), _opt(bias, name='bias'), _opt(residual, BF16, 'residual'),
           N, H, W, Cin, Cout, cout_pad, taps, _opt(y, BF16, 'y'), y_ld, _opt(y_nchw, name='y_nchw'), _opt(stats, name='stats'),
           groups, _stream())
 
 
-def conv_wgrad(dy, x, N, H, W, x_C, Cin, dy_C, Cout, taps, dw):
+def conv_wgrad(dy, x, N, H, W, x_C, Cin, dy_C, Cout, taps, dw, gn=None):
+    """gn: as in conv_fwd -- the gradient is taken against relu(groupnorm(x))."""
+    if gn is not None:
+        gst, gamma, beta, G, eps = gn
+        if taps != 1:
+            raise RuntimeError('conv_wgrad: only 1x1 layers take a fused input GroupNorm')
+        _call('sh_conv_wgrad_gn', _chk(dy, BF16, 'dy'), _chk(x, BF16, 'x'), _chk(gst, name='gn_stats'), _chk(gamma, name='gamma'),
+              _chk(beta, name='beta'), G, eps, N, H, W, x_C, Cin, dy_C, Cout, _chk(dw, name='dw'), _stream())
+        return
     _call('sh_conv_wgrad', _chk(dy, BF16, 'dy'), _chk(x, BF16, 'x'), N, H, W, x_C, Cin, dy_C, Cout, taps, _chk(dw, name='dw'),
           _stream())
 

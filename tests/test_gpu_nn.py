@@ -94,6 +94,48 @@ def test_conv_fwd_dgrad_wgrad(N, H, Cin, Cout, taps):
         assert rel_err((dw2 - 1).cpu(), ref_dw.cpu()) < 2e-3
 
 
+@pytest.mark.parametrize('N,H,Cin,Cout,res', [(3, 32, 128, 64, False), (5, 8, 256, 128, False), (2, 64, 64, 128, True), (7, 16, 128, 256, True),
+                                              (37, 8, 64, 128, True), (1, 16, 256, 128, False)])
+def test_conv1x1_with_fused_input_groupnorm(N, H, Cin, Cout, res):
+    """sh_conv_fwd_gn / sh_conv_wgrad_gn (GroupNorm + ReLU applied to the operand tiles in shared memory) against the two-pass
+    path sh_gn_relu_fwd -> sh_conv_fwd / sh_conv_wgrad on the same inputs: the forward is BIT-identical (same scale / shift
+    expression, same bf16 rounding of the normalised operand, same MMA schedule); the weight gradient differs by atomics order only."""
+    torch.manual_seed(N * 131 + H + Cin)
+    x = (torch.randn(N, H, H, Cin, device=DEV) * 1.7 + 0.4).to(BF16)
+    gamma = torch.rand(Cin, device=DEV) + 0.5
+    beta = torch.randn(Cin, device=DEV) * 0.3
+    stx = stats_of(x, 16)
+    w = torch.randn(Cout, Cin, 1, 1, device=DEV) / Cin ** 0.5
+    b = torch.randn(Cout, device=DEV)
+    r = torch.randn(N, H, H, Cout, device=DEV).to(BF16) if res else None
+    cout_pad = (Cout + 127) // 128 * 128 if Cout > 64 else 64
+    b_rows = (Cin + 127) // 128 * 128 if Cin > 64 else 64
+    b_cols = (Cout + 63) // 64 * 64
+    wf = torch.empty((1, cout_pad, Cin), device=DEV, dtype=BF16)
+    wb = torch.empty((1, b_rows, b_cols), device=DEV, dtype=BF16)
+    ops.pack_weights(w, Cout, Cin, 1, cout_pad, Cin, wf, wb, b_rows, b_cols)
+    a = torch.empty_like(x)
+    ops.gn_relu_fwd(x, stx, gamma, beta, N, H * H, Cin, 16, a)
+    out = {}
+    for fused in (False, True):
+        y = torch.zeros((N, H, H, Cout), device=DEV, dtype=BF16)
+        st = torch.zeros((N, 16, 2), device=DEV)
+        ops.conv_fwd(x if fused else a, wf, b, N, H, H, Cin, Cout, cout_pad, 1, y=y, y_ld=Cout, residual=r, stats=st, groups=16,
+                     gn=(stx, gamma, beta, 16, 1e-5) if fused else None)
+        dy = torch.randn(N, H, H, Cout, generator=torch.Generator(device=DEV).manual_seed(5), device=DEV).to(BF16)
+        dw = torch.zeros_like(w)
+        ops.conv_wgrad(dy, x if fused else a, N, H, H, Cin, Cin, Cout, Cout, 1, dw, gn=(stx, gamma, beta, 16, 1e-5) if fused else None)
+        torch.cuda.synchronize()
+        out[fused] = (y, st, dw)
+    assert torch.equal(out[True][0], out[False][0]), (out[True][0].float() - out[False][0].float()).abs().max()
+    assert rel_err(out[True][1].cpu(), out[False][1].cpu()) < 1e-4
+    assert rel_err(out[True][2].cpu(), out[False][2].cpu()) < 1e-4
+    ref = F.conv2d(nchw(a), w.to(BF16).float(), b) + (nchw(r) if res else 0)
+    assert rel_err(nchw(out[True][0]).cpu(), ref.cpu()) < 1e-2
+    # the raw operand was left untouched in HBM
+    assert torch.equal(stats_of(x, 16), stx)
+
+
 @pytest.mark.parametrize('N,H,W,Cin,Cout', [(40, 32, 32, 128, 128), (19, 16, 16, 128, 128), (5, 64, 64, 64, 64), (75, 16, 8, 256, 128),
                                             (2, 32, 32, 128, 82)])
 def test_conv3x3_halo_mode(N, H, W, Cin, Cout):

@@ -16,7 +16,7 @@ from spherehand_b200.engine import SelfSupTrainStep                # noqa: E402
 from spherehand_b200.model import HandModel                        # noqa: E402
 from spherehand_b200.network.hourglass import create_hourglass_network   # noqa: E402
 
-SHAPE_ARGS = {'sh_conv_fwd': (4, 5, 6, 7, 8, 10), 'sh_conv_wgrad': (2, 3, 4, 6, 8, 9), 'sh_conv_wgrad3x3': (2, 3, 4, 6, 8),
+SHAPE_ARGS = {'sh_conv_fwd': (4, 5, 6, 7, 8, 10), 'sh_conv_fwd_gn': (9, 10, 11, 12, 13), 'sh_conv_wgrad_gn': (7, 8, 9, 11, 13), 'sh_conv_wgrad': (2, 3, 4, 6, 8, 9), 'sh_conv_wgrad3x3': (2, 3, 4, 6, 8),
               'sh_gn_relu_fwd': (4, 5, 6), 'sh_gn_relu_bwd_prezeroed': (6, 7, 8), 'sh_maxpool_fwd': (1, 2, 3, 4), 'sh_maxpool_bwd': (3, 4, 5, 6),
               'sh_upsample_add_fwd': (2, 3, 4, 5), 'sh_upsample_bwd': (1, 2, 3, 4), 'sh_add': (3, 4, 5), 'sh_colsum': (1, 2, 3)}
 
@@ -43,7 +43,7 @@ def main():
     prof, _lib.PROFILE = _lib.PROFILE, None
     agg = {}
     for name, a, e0, e1 in prof:
-        key = (name,) + tuple(a[i] for i in SHAPE_ARGS.get(name, ())) + ((bool(a[3]),) if name == 'sh_conv_fwd' else ()) + \
+        key = (name,) + tuple(a[i] for i in SHAPE_ARGS.get(name, ())) + ((bool(a[3]),) if name == 'sh_conv_fwd' else ()) + ((bool(a[8]),) if name == 'sh_conv_fwd_gn' else ()) + \
               ((bool(a[5]),) if name == 'sh_gn_relu_bwd_prezeroed' else ())
         fl, by, fam = bench.call_work(name, a)
         d = agg.setdefault(key, [0, 0.0, 0.0, 0.0, fam])
