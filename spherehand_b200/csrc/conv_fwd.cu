@@ -24,10 +24,10 @@
 //     HBM-bound 1x1 layers (ncu: the MMA and the TMA ring wait on it), and a warp cannot hide its own dependent-issue
 //     latencies; group (b, h) serves accumulator buffer b (alternate tiles) and the 64-channel chunks c = h, h+2, ...
 //     of it, 32 columns at a time (register budget of a 576-thread CTA), with its own staging slot.
-// Warp roles (704 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..17 = epilogue groups 0..3 (4 warps each, one TMEM lane quadrant per warp), warps 18..21 = operand transform
-// (fused GroupNorm + ReLU of a 1x1 layer's input, applied to every A tile in shared memory between the TMA arrival and the MMA;
-// idle otherwise).
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..17 = epilogue groups 0..3 (4 warps each, one TMEM lane quadrant per warp).  The XF build (sh_conv_fwd_gn, 704 threads)
+// adds warps 18..21 = operand transform: the fused GroupNorm + ReLU of a 1x1 layer's input, applied to every A tile in shared
+// memory between the TMA arrival and the MMA.
 #include "tc_common.cuh"
 
 namespace {
@@ -35,7 +35,7 @@ namespace {
 constexpr int kBM = 128;           // pixels per tile = TMEM lanes
 constexpr int kBK = 64;            // channels per k-block = one 128-byte swizzle row
 constexpr int kThreads = 576;       // producer + MMA + 16 epilogue warps
-constexpr int kThreadsXf = 704;     // + 4 operand-transform warps (fused GroupNorm of a 1x1 layer's input): the non-halo build
+constexpr int kThreadsXf = 704;     // + 4 operand-transform warps (fused GroupNorm of a 1x1 layer's input): the XF build
 constexpr int kMaxStages = 8;
 constexpr int kGroups = 4;         // epilogue warp-groups, one 16 KB staging slot each
 constexpr int kABytes = kBM * kBK * 2;          // 16 KB
@@ -156,8 +156,8 @@ __device__ __forceinline__ void row_stats(const uint32_t (&packed)[NW], bool row
     }
 }
 
-template <int BN, bool HALO>
-__global__ void __launch_bounds__(HALO ? kThreads : kThreadsXf, 1) conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, bool HALO, bool XF>
+__global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmRes,
                                                                const __grid_constant__ CUtensorMap tmOut,
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(HALO ? kThreads : kThreadsXf, 1) conv_fwd_kern
         // a buffer is drained by one group (single-chunk layers) or by the two groups that split its chunks
         for (int b = 0; b < 4; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], g.nchunks >= 2 ? 256 : 128); }
         for (int s = 0; s < kHaloSlots; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], 1); }
-        for (int s = 0; s < kMaxStages; ++s) mbar_init(&xf_bar[s], 32);
+        for (int s = 0; s < kMaxStages; ++s) mbar_init(&xf_bar[s], 128);
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = (p.bias && i < g.cout) ? p.bias[i] : 0.f;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(HALO ? kThreads : kThreadsXf, 1) conv_fwd_kern
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
                 for (int k = 0; k < num_k; ++k, ++it) {
                     const int s = it % g.stages, ph = (it / g.stages) & 1;
-                    mbar_wait(g.fuse_gn ? &xf_bar[s] : &full_bar[s], ph);
+                    mbar_wait(XF ? &xf_bar[s] : &full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(s_pipe + s * stage_bytes);
                     const uint32_t b_addr = g.b_resident ? smem_u32(s_bres + k * kBBytes) : a_addr + kABytes;
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(HALO ? kThreads : kThreadsXf, 1) conv_fwd_kern
                     const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(s_ident));
                     for (int c = 0; c < g.nchunks; ++c, ++it) {
                         const int s = it % g.stages, ph = (it / g.stages) & 1;
-                        mbar_wait(g.fuse_gn ? &xf_bar[s] : &full_bar[s], ph);
+                        mbar_wait(XF ? &xf_bar[s] : &full_bar[s], ph);
                         tc_fence_after();
                         const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(s_pipe + s * stage_bytes));
 #pragma unroll
@@ -370,39 +370,36 @@ __global__ void __launch_bounds__(HALO ? kThreads : kThreadsXf, 1) conv_fwd_kern
                 umma_commit(&acc_full[buf]);                    // accumulator complete
             }
         }
-    } else if (warp >= 18) {
+    } else if (XF && warp >= 18) {
         // ===================== operand transform: A := relu(groupnorm(x)) in shared memory =====================
-        if (!HALO && g.fuse_gn) {
-            // one warp per pipeline stage (4 stages in flight): the transform of a tile is a chain of dependent latencies (scale /
-            // shift loads -> barrier wait -> shared-memory round trip), so four tiles must overlap to keep up with the TMA ring
-            // A stage always belongs to the same warp, so a warp meets the phases of its barriers in order.
-            const int xw = warp - 18;                           // this warp owns the stages s % 4 == xw
-            const int j = lane & 7, r0 = lane >> 3;             // 16-byte chunk of the 128-byte rows; rows r0, r0+4, ..., r0+124
+        if constexpr (XF) {
+            // All four warps work on the same stage: what matters is the LATENCY from "tile landed" to "tile transformed" (it is
+            // added to every trip of the TMA ring, whose depth bounds the bandwidth of these layers), not the warps' throughput.
+            const int tt = (int)threadIdx.x - 18 * 32;          // 0..127
+            const int j = tt & 7, r = tt >> 3;                  // 16-byte chunk of the 128-byte rows; rows r + 16 i
             int it = 0;
             for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
                 const TileCoord t = tile_coord(g, tile);
                 const int nA = min(t.n0, g.N - 1), nB = min(t.n0 + g.bn - 1, g.N - 1);   // rows 0..63 / 64..127 (bn <= 2)
                 for (int k = 0; k < num_k; ++k, ++it) {         // taps == 1: k is the 64-channel block
                     const int s = it % g.stages, ph = (it / g.stages) & 1;
-                    if ((s & 3) != xw) continue;
                     float ka[8], kb[8];
                     gn_scale_shift(p.gn, nA, k * kBK + j * 8, ka, kb);                   // (global loads: issued before the wait)
                     mbar_wait(&full_bar[s], ph);
                     const uint32_t tileA = smem_u32(s_pipe + s * stage_bytes);
-#pragma unroll 1
-                    for (int h = 0; h < 2; ++h) {                                        // rows 0..63 (image nA), 64..127 (image nB)
-                        if (h == 1 && nB != nA) gn_scale_shift(p.gn, nB, k * kBK + j * 8, ka, kb);
-                        gn_xform_rows<16>(tileA + h * 64 * 128, r0, j, ka, kb);
-                    }
+                    gn_xform_rows4(tileA, r, j, ka, kb);                                 // rows 0..63   (image nA)
+                    if (nB != nA) gn_scale_shift(p.gn, nB, k * kBK + j * 8, ka, kb);
+                    gn_xform_rows4(tileA + 64 * 128, r, j, ka, kb);                      // rows 64..127 (image nB)
                     fence_async_smem();                         // generic-proxy writes -> visible to tcgen05.mma
                     mbar_arrive(&xf_bar[s]);
                 }
                 if (g.has_res) {                                // the residual tiles ride the same ring untransformed
                     for (int c = 0; c < g.nchunks; ++c, ++it) {
                         const int s = it % g.stages, ph = (it / g.stages) & 1;
-                        if ((s & 3) != xw) continue;
-                        mbar_wait(&full_bar[s], ph);
-                        mbar_arrive(&xf_bar[s]);
+                        if (tt == 0) {
+                            mbar_wait(&full_bar[s], ph);
+                            mbar_arrive_n(&xf_bar[s], 128);     // (the barrier counts the 128 transform threads)
+                        }
                     }
                 }
             }
@@ -431,7 +428,7 @@ __global__ void __launch_bounds__(HALO ? kThreads : kThreadsXf, 1) conv_fwd_kern
             const bool row_ok = n < g.N;
             const int tl = buf + 2 * lt;                        // local tile index; its accumulator and barrier phase
             const int abuf = tl & (NACC - 1);
-            mbar_wait_polite(&acc_full[abuf], (uint32_t)((tl / NACC) & 1));
+            mbar_wait(&acc_full[abuf], (uint32_t)((tl / NACC) & 1));
             tc_fence_after();
             for (int c = half; c < g.nchunks; c += 2) {
                 const int cg = c * 64;                          // first channel of this chunk
@@ -517,15 +514,15 @@ int make_act_tmap(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
     return sh_make_tmap_bf16(m, base, 4, dims, strides, box);
 }
 
-template <int BN, bool HALO>
+template <int BN, bool HALO, bool XF = false>
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmRes, const CUtensorMap& tmOut,
                 const ConvGeom& g, const ConvPtrs& p, int grid, size_t smem, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        SH_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        SH_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<BN, HALO, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr = true;
     }
-    conv_fwd_kernel<BN, HALO><<<grid, HALO ? kThreads : kThreadsXf, smem, st>>>(tmA, tmB, tmRes, tmOut, g, p);
+    conv_fwd_kernel<BN, HALO, XF><<<grid, XF ? kThreadsXf : kThreads, smem, st>>>(tmA, tmB, tmRes, tmOut, g, p);
     SH_CHECK_LAUNCH("conv_fwd_kernel");
     return SH_OK;
 }
@@ -621,6 +618,11 @@ static int conv_fwd_impl(const void* x, const void* w, const void* bias, const v
     if (halo) {
         if (cout_pad == 128) return launch_conv<128, true>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
         return launch_conv<64, true>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+    }
+    if (g.fuse_gn) {            // the build with the four operand-transform warps (704 threads, 80 registers)
+        if (cout_pad == 256) return launch_conv<256, false, true>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+        if (cout_pad == 128) return launch_conv<128, false, true>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
+        return launch_conv<64, false, true>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
     }
     if (cout_pad == 256) return launch_conv<256, false>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);
     if (cout_pad == 128) return launch_conv<128, false>(tmA, tmB, tmRes, tmOut, g, p, grid, smem, st);

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad1x1_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmDY);
         tma_prefetch_desc(&tmX);
-        for (int s = 0; s < kW1MaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&xf_bar[s], 32); }
+        for (int s = 0; s < kW1MaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&xf_bar[s], 128); }
         mbar_init(accum_bar, 1);
         mbar_fence_init();
     }
@@ -303,21 +303,20 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad1x1_kernel(const __grid_cons
         if (g.fuse_gn) {
             // the four epilogue warps are idle until the accumulator is complete: they apply GroupNorm + ReLU to the X chunks of
             // every stage in shared memory (X in HBM is the raw GroupNorm input; its normalised form is never materialised)
-            // One warp per stage, four stages in flight (the chain scale / shift loads -> wait -> shared-memory round trip is latency).
-            // A stage always belongs to the same warp, so a warp meets the phases of its barriers in order.
-            const int xw = warp - 2;                            // this warp owns the stages s % 4 == xw
-            const int j = lane & 7, r0 = lane >> 3;             // 16-byte chunk of the 128-byte rows; rows r0, r0+4, ..., r0+60
+            // All four warps work on the same stage: the latency "tile landed -> tile transformed" is added to every trip of the ring.
+            const int tt = (int)threadIdx.x - 64;               // 0..127
+            const int j = tt & 7, r = tt >> 3;                  // 16-byte chunk of the 128-byte rows; rows r, r+16, r+32, r+48
             const int tiles_per_img = g.tiles_w * g.tiles_h;    // bn == 1
+            static_assert(kWPix == 64, "the transform covers a 64-pixel slab per 64-channel chunk");
             for (int k = 0; k < num_k; ++k) {
                 const int s = k % g.stages, it = k / g.stages;
-                if ((s & 3) != xw) continue;
                 const int n = min((tile_begin + k) / tiles_per_img, g.N - 1);
-                uint8_t* b_dst = smem + s * g.stage_bytes + a_bytes;
+                const uint32_t b_dst = smem_u32(smem + s * g.stage_bytes + a_bytes);
                 for (int c = 0; c < g.cin_pad / 64; ++c) {
                     float ka[8], kb[8];
                     gn_scale_shift(g.gn, n, c * 64 + j * 8, ka, kb);          // (global loads: issued before the wait)
                     if (c == 0) mbar_wait(&full_bar[s], it & 1);
-                    gn_xform_rows<kWPix / 4>(smem_u32(b_dst + c * kWPix * 128), r0, j, ka, kb);
+                    gn_xform_rows4(b_dst + c * kWPix * 128, r, j, ka, kb);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&xf_bar[s]);

@@ -30,6 +30,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -38,21 +41,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra D_%=;\n\t"
         "bra W_%=;\n\t"
         "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-// The same wait for warps whose wake-up latency does not matter (a whole epilogue group waiting microseconds for its accumulator):
-// the bare try_wait loop above re-issues every few cycles, and 16 such warps take most of the issue slots of the 4 schedulers away from
-// the warps that have arithmetic to do (ncu: 70 % of a 1x1 layer's executed instructions were this loop).  Here the thread is
-// suspended by the hardware for up to the hinted time, then backs off with nanosleep.
-__device__ __forceinline__ void mbar_wait_polite(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra D_%=;\n\t"
-        "nanosleep.u32 64;\n\t"
-        "bra W_%=;\n\t"
-        "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(2000u) : "memory");
 }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
@@ -139,33 +127,26 @@ __device__ __forceinline__ void gn_scale_shift(const GnOperand& q, int n, int c0
         kb[e] = fmaf(-mu, ka[e], be[e]);
     }
 }
-// NR rows r0, r0+4, r0+8, ... (r0 < 4) of chunk j of the tile at shared address `tile`: relu(bf16(x * ka + kb)), in place.  Explicit
-// shared-space 128-bit accesses, four rows in flight (the loads of a batch are issued before its arithmetic: the loop is otherwise a
-// chain of shared-memory round trips), the ReLU folded into the bf16 conversion (round, then clamp == clamp, then round).
-template <int NR>
-__device__ __forceinline__ void gn_xform_rows(uint32_t tile, int r0, int j, const float (&ka)[8], const float (&kb)[8]) {
-    static_assert(NR % 4 == 0, "rows are processed four at a time");
-    const uint32_t a_even = tile + (uint32_t)(r0 * 128 + ((j ^ r0) << 4));                 // rows r0 + 8m:     row & 7 == r0
-    const uint32_t a_odd = tile + (uint32_t)((r0 + 4) * 128 + ((j ^ (r0 + 4)) << 4));      // rows r0 + 4 + 8m: row & 7 == r0 + 4
-#pragma unroll 1
-    for (int i = 0; i < NR; i += 4) {                    // (rolled: the unrolled form thrashes the instruction cache between roles)
-        uint32_t v[4][4];
+// Rows r, r+16, r+32, r+48 (r < 16) of chunk j of the tile at shared address `tile`: relu(bf16(x * ka + kb)), in place.  128 threads
+// cover a 64-row slab this way (thread t: j = t & 7, r = t >> 3), so the time from "tile landed" to "tile transformed" is one batch
+// of four shared-memory round trips: that latency is added to every trip of the TMA ring, whose depth bounds the kernel's bandwidth.
+// Explicit shared-space 128-bit accesses, the four loads issued before the arithmetic, the ReLU folded into the bf16 conversion
+// (round, then clamp == clamp, then round).
+__device__ __forceinline__ void gn_xform_rows4(uint32_t tile, int r, int j, const float (&ka)[8], const float (&kb)[8]) {
+    const uint32_t a0 = tile + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));                 // (r + 16 i) & 7 == r & 7
+    uint32_t v[4][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t addr = ((u & 1) ? a_odd : a_even) + (uint32_t)(((i + u) >> 1) * 1024);
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]) : "r"(addr) : "memory");
+    for (int u = 0; u < 4; ++u)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]) : "r"(a0 + u * 2048));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 y = __ffma2_rn(make_float2(__uint_as_float(v[u][e] << 16), __uint_as_float(v[u][e] & 0xffff0000u)),
+                                        make_float2(ka[2 * e], ka[2 * e + 1]), make_float2(kb[2 * e], kb[2 * e + 1]));
+            asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(v[u][e]) : "f"(y.y), "f"(y.x));
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 y = __ffma2_rn(make_float2(__uint_as_float(v[u][e] << 16), __uint_as_float(v[u][e] & 0xffff0000u)),
-                                            make_float2(ka[2 * e], ka[2 * e + 1]), make_float2(kb[2 * e], kb[2 * e + 1]));
-                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(v[u][e]) : "f"(y.y), "f"(y.x));
-            }
-            const uint32_t addr = ((u & 1) ? a_odd : a_even) + (uint32_t)(((i + u) >> 1) * 1024);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[u][0]), "r"(v[u][1]), "r"(v[u][2]), "r"(v[u][3]) : "memory");
-        }
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0 + u * 2048), "r"(v[u][0]), "r"(v[u][1]), "r"(v[u][2]), "r"(v[u][3]));
     }
 }
 

@@ -344,13 +344,14 @@ def test_hourglass_backward_uses_its_own_forward_tape():
     def l2(a, b):
         return float((a - b).double().norm() / b.double().norm().clamp_min(1e-30))
     runs = []
-    for _ in range(2):
+    for _ in range(4):
         net.zero_grad()
         o, _ = net(x1)
         (o[0] * w).sum().backward()
         runs.append({k: p.grad.clone() for k, p in net.named_parameters()})
     want = runs[0]
-    floor = {k: l2(runs[1][k], want[k]) for k in want}    # run-to-run noise of the same pass (fp32 atomics order -> bf16 flips)
+    # run-to-run noise of the same pass (fp32 atomics order -> bf16 flips), worst of three repeats: single small tensors move by several %
+    floor = {k: max(l2(r[k], want[k]) for r in runs[1:]) for k in want}
     net.zero_grad()
     o1, _ = net(x1)
     o2, _ = net(x2)                                   # a later forward with another batch size
@@ -359,7 +360,10 @@ def test_hourglass_backward_uses_its_own_forward_tape():
     (o1[0] * w).sum().backward()
     worst = max((l2(p.grad, want[k]) - 3 * floor[k], k) for k, p in net.named_parameters())
     print('own-tape backward vs a plain forward/backward: worst excess over 3x the run-to-run floor', worst, 'largest floor', max(floor.values()))
-    assert worst[0] < 2e-2, worst
+    assert worst[0] < 5e-2, worst
+    allg = lambda d: torch.cat([d[k].flatten() for k in want])
+    agg, agg_floor = l2(allg({k: p.grad for k, p in net.named_parameters()}), allg(want)), max(l2(allg(r), allg(want)) for r in runs[1:])
+    assert agg < 2 * agg_floor + 1e-2, (agg, agg_floor)
     # a wrong tape (the batch-3 forward's) would not even have the right shapes; a stale one of the same shape would be ~100 % off
     (o2[0] * 0.5).sum().backward()                    # the second node still has its own tape
     with pytest.raises(RuntimeError):
