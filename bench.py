@@ -186,11 +186,13 @@ def call_work(name, a):
 
 
 FAMILY_KERNELS = {
-    'conv1x1': ('conv_fwd_kernel (tcgen05 implicit-GEMM convolution, forward + data-gradient launches), 1x1 layers', 'hbm'),
+    'conv1x1': ('conv_fwd_kernel (tcgen05 implicit-GEMM convolution, forward + data-gradient launches; incl. the launches that apply the '
+                'preceding GroupNorm + ReLU to their operand tiles in shared memory), 1x1 layers', 'hbm'),
     'conv3x3': ('conv_fwd_kernel (tcgen05 implicit-GEMM convolution, forward + data-gradient launches), 3x3 layers', 'tensor'),
-    'wgrad1x1': ('wgrad1x1_kernel / wgrad_kernel (tcgen05 weight gradient), 1x1 layers', 'hbm'),
+    'wgrad1x1': ('wgrad1x1_kernel / wgrad_kernel (tcgen05 weight gradient; incl. the fused-GroupNorm-operand launches), 1x1 layers', 'hbm'),
     'wgrad3x3': ('wgrad3x3_kernel / wgrad_kernel (tcgen05 weight gradient), 3x3 layers', 'tensor'),
-    'gn_relu_fwd': ('gn_relu_fwd_kernel (GroupNorm + ReLU apply; statistics come from the producer)', 'hbm'),
+    'gn_relu_fwd': ('gn_relu_fwd_kernel (GroupNorm + ReLU apply where it is not folded into the consuming 1x1 layer; statistics come from '
+                    'the producer)', 'hbm'),
     'gn_relu_bwd': ('gn_relu_bwd_kernel (GroupNorm + ReLU backward, one pass, fused residual add + bias column sum)', 'hbm'),
     'pool_upsample_add': ('maxpool / upsample+add / add kernels, forward and backward', 'hbm'),
     'mvproj': ('mvproj_main_kernel (MutualProjectionLoss fwd+bwd: transform, sphere render, both loss terms, analytic gradient)', 'hbm'),

@@ -27,6 +27,10 @@ def tag(name, a):
         return 'sh_conv_fwd_%s' % ('3x3' if a[10] == 9 else '1x1')
     if name == 'sh_conv_wgrad':
         return 'sh_conv_wgrad_%s' % ('3x3' if a[9] == 9 else '1x1')
+    if name == 'sh_conv_fwd_gn':            # the 1x1 layer with the GroupNorm in front of it folded in: same family
+        return 'sh_conv_fwd_1x1'
+    if name == 'sh_conv_wgrad_gn':
+        return 'sh_conv_wgrad_1x1'
     return name
 
 
