@@ -655,64 +655,70 @@ __global__ void __launch_bounds__(kT) colsum_kernel(const __nv_bfloat16* __restr
 constexpr int kStemCols = 64;                 // output columns per block
 constexpr int kStemRows = 2;                  // output rows per block
 constexpr int kStemPatchW = 2 * kStemCols + 4;
-__global__ void __launch_bounds__(kT) stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ wgt,
+constexpr int kStemUnits = 4;                 // row pairs per block: the [tap][co] weights are gathered once for all of them
+__global__ void __launch_bounds__(kT, 3) stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ wgt,
                                                            const float* __restrict__ bias, int S, __nv_bfloat16* __restrict__ y,
                                                            float* __restrict__ stats_out, int G_out) {
-    __shared__ __align__(16) float s_w[25 * 64];          // [tap][co]
+    // weights as [tap][half][cv][4]: a thread's two float4 (channels c0..c0+3, c0+4..c0+7) are each one conflict-free 128-byte
+    // wavefront across the 8 channel vectors (the [tap][co] form put cv and cv+4 on the same banks: 13 M conflicts per launch)
+    __shared__ __align__(16) float s_w[25 * 64];
     __shared__ float s_in[(2 * kStemRows + 3) * kStemPatchW];
     __shared__ float s_st[8][8];
     const int n = blockIdx.z, O = S / 2;
-    const int oh0 = blockIdx.y * kStemRows, ow0 = blockIdx.x * kStemCols;
-    for (int i = threadIdx.x; i < 25 * 64; i += kT) s_w[i] = wgt[(i % 64) * 25 + i / 64];
-    for (int i = threadIdx.x; i < (2 * kStemRows + 3) * kStemPatchW; i += kT) {
-        const int r = i / kStemPatchW, c = i - r * kStemPatchW;
-        const int ih = 2 * oh0 - 2 + r, iw = 2 * ow0 - 2 + c;
-        s_in[i] = (ih >= 0 && ih < S && iw >= 0 && iw < S) ? __ldg(img + ((size_t)n * S + ih) * S + iw) : 0.f;
+    const int ow0 = blockIdx.x * kStemCols;
+    for (int i = threadIdx.x; i < 25 * 64; i += kT) {
+        const int tap = i >> 6, co = i & 63;
+        s_w[tap * 64 + ((co >> 2) & 1) * 32 + (co >> 3) * 4 + (co & 3)] = wgt[co * 25 + tap];
     }
-    __syncthreads();
     const int cv = threadIdx.x & 7, q = threadIdx.x >> 3;            // 8 channel vectors x 32 pixel quads
     const int c0 = cv * 8;
     const int lr = q / (kStemCols / 4), lc = (q % (kStemCols / 4)) * 4;   // local output row, first local output column
-    float2 acc2[4][4];                                               // [pixel][channel pair]: packed FFMA2, one issue slot per pair
+    float st[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int u = 0; u < kStemUnits; ++u) {
+        const int oh0 = (blockIdx.y * kStemUnits + u) * kStemRows;
+        if (oh0 >= O) break;                                         // block-uniform
+        __syncthreads();                                             // the previous unit's patch has been consumed (and s_w is written)
+        for (int i = threadIdx.x; i < (2 * kStemRows + 3) * kStemPatchW; i += kT) {
+            const int r = i / kStemPatchW, c = i - r * kStemPatchW;
+            const int ih = 2 * oh0 - 2 + r, iw = 2 * ow0 - 2 + c;
+            s_in[i] = (ih >= 0 && ih < S && iw >= 0 && iw < S) ? __ldg(img + ((size_t)n * S + ih) * S + iw) : 0.f;
+        }
+        __syncthreads();
+        float2 acc2[4][4];                                           // [pixel][channel pair]: packed FFMA2, one issue slot per pair
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc2[i][e] = make_float2(bias[c0 + 2 * e], bias[c0 + 2 * e + 1]);
+            for (int e = 0; e < 4; ++e) acc2[i][e] = make_float2(bias[c0 + 2 * e], bias[c0 + 2 * e + 1]);
 #pragma unroll
-    for (int kh = 0; kh < 5; ++kh) {
-        float in[11];
-        const float* row = s_in + (2 * lr + kh) * kStemPatchW + 2 * lc;
+        for (int kh = 0; kh < 5; ++kh) {
+            float in[11];
+            const float* row = s_in + (2 * lr + kh) * kStemPatchW + 2 * lc;
 #pragma unroll
-        for (int j = 0; j < 11; ++j) in[j] = row[j];
+            for (int j = 0; j < 11; ++j) in[j] = row[j];
 #pragma unroll
-        for (int kw = 0; kw < 5; ++kw) {
-            const float4 w0 = *reinterpret_cast<const float4*>(s_w + (kh * 5 + kw) * 64 + c0);
-            const float4 w1 = *reinterpret_cast<const float4*>(s_w + (kh * 5 + kw) * 64 + c0 + 4);
-            const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
+            for (int kw = 0; kw < 5; ++kw) {
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w + (kh * 5 + kw) * 64 + cv * 4);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_w + (kh * 5 + kw) * 64 + 32 + cv * 4);
+                const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 iv = make_float2(in[2 * i + kw], in[2 * i + kw]);
+                for (int i = 0; i < 4; ++i) {
+                    const float2 iv = make_float2(in[2 * i + kw], in[2 * i + kw]);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) acc2[i][e] = __ffma2_rn(iv, wv[e], acc2[i][e]);
+                    for (int e = 0; e < 4; ++e) acc2[i][e] = __ffma2_rn(iv, wv[e], acc2[i][e]);
+                }
             }
         }
-    }
-    float acc[4][8];
+        const int oh = oh0 + lr;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) {
+            const int ow = ow0 + lc + i;
+            if (oh < O && ow < O) {
+                bf8 v;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { acc[i][2 * e] = acc2[i][e].x; acc[i][2 * e + 1] = acc2[i][e].y; }
-    const int oh = oh0 + lr;
-    float st[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int ow = ow0 + lc + i;
-        if (oh < O && ow < O) {
-            bf8 v;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v.v[e] = acc[i][e];
-            store8(y + (((size_t)n * O + oh) * O + ow) * 64 + c0, v);
-            if (stats_out) stats_accum(st, v, 64 / G_out);
+                for (int e = 0; e < 4; ++e) { v.v[2 * e] = acc2[i][e].x; v.v[2 * e + 1] = acc2[i][e].y; }
+                store8(y + (((size_t)n * O + oh) * O + ow) * 64 + c0, v);
+                if (stats_out) stats_accum(st, v, 64 / G_out);
+            }
         }
     }
     if (stats_out) {
@@ -1089,7 +1095,7 @@ SH_EXPORT int sh_stem_conv_fwd(const void* img, const void* w, const void* b, in
     SH_REQUIRE(N <= 65535, "sh_stem_conv_fwd: N > 65535");
     if (N == 0) return SH_OK;
     const int O = S / 2;
-    dim3 grid(sh_div_up(O, kStemCols), sh_div_up(O, kStemRows), N);
+    dim3 grid(sh_div_up(O, kStemCols), sh_div_up(O, kStemRows * kStemUnits), N);
     stem_conv_fwd_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const float*)img, (const float*)w, (const float*)b, S,
                                                                 (__nv_bfloat16*)y, (float*)stats_out, G_out);
     SH_CHECK_LAUNCH("stem_conv_fwd_kernel");

@@ -331,6 +331,39 @@ def test_hourglass_golden(stacks):
         assert med < (0.25 if kind == 'noise' else 0.03)
 
 
+def test_hourglass_with_fused_groupnorm_equals_two_pass_network():
+    """The whole 2-stack network with GroupNorm + ReLU folded into the bottleneck 1x1 layers (default) against the two-pass network
+    (SH_FUSE_GN=0 path).  Each fused convolution is bit-identical to its two-pass form on the same operands
+    (test_conv1x1_with_fused_input_groupnorm); through the network the GroupNorm statistics are fp32 atomic sums whose order differs
+    from run to run, so the yardstick for heat-maps and parameter gradients is the run-to-run difference of the two-pass network."""
+    from spherehand_b200.network import hourglass as hg
+    from oracle.hourglass import det_state_dict, det_uniform
+    net = hg.create_hourglass_network(82, 2).to(DEV)
+    net.load_state_dict(det_state_dict(82, 2, seed=3))
+    x = torch.from_numpy(det_uniform(5 * 128 * 128, 4).reshape(5, 128, 128)).to(DEV)
+    w = [torch.from_numpy(det_uniform(5 * 82 * 32 * 32, 5 + i).reshape(5, 82, 32, 32)).to(DEV) for i in range(2)]
+    def run(fused):
+        old, hg.FUSE_GN = hg.FUSE_GN, fused
+        try:
+            net.zero_grad()
+            o, _ = net(x)
+            (o[0] * w[0] + o[1] * w[1]).sum().backward()
+        finally:
+            hg.FUSE_GN = old
+        return [t.detach().clone() for t in o], torch.cat([p.grad.flatten() for p in net.parameters()])
+    o_f, g_f = run(True)
+    o_u, g_u = run(False)
+    o_u2, g_u2 = run(False)
+    nrm = lambda a, b: float((a - b).double().norm() / b.double().norm())
+    for i in range(2):
+        floor = nrm(o_u2[i], o_u[i])
+        print('stack %d heat-maps, fused vs two-pass: %.3e (two-pass run-to-run: %.3e)' % (i, nrm(o_f[i], o_u[i]), floor))
+        assert nrm(o_f[i], o_u[i]) < 2 * floor + 1e-3
+    floor = nrm(g_u2, g_u)
+    print('fused vs two-pass gradients: %.3e (two-pass run-to-run: %.3e)' % (nrm(g_f, g_u), floor))
+    assert nrm(g_f, g_u) < 2 * floor + 1e-3
+
+
 def test_hourglass_backward_uses_its_own_forward_tape():
     """Two forwards (different batch sizes) before a backward, and a no-grad forward in between: each autograd node must
     back-propagate through the activations of ITS forward (the tape used to be the most recent forward's)."""
