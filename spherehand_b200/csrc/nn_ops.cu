@@ -638,10 +638,22 @@ __global__ void __launch_bounds__(kT) colsum_kernel(const __nv_bfloat16* __restr
 #pragma unroll
     for (int e = 0; e < 8; ++e) cs[e] = 0.f;
     const int p_end = min((int)(blockIdx.x + 1) * ppb, HW);
-    for (int pp = blockIdx.x * ppb + w.r; pp < p_end; pp += w.rows) {
-        const bf8 r = load8(x + ((size_t)n * HW + pp) * C + c0);
+    constexpr int kU = 4;                        // independent 16-byte loads in flight per thread (a pure read: nothing else hides them)
+    for (int p0 = blockIdx.x * ppb + w.r; p0 < p_end; p0 += w.rows * kU) {
+        uint4 raw[kU];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) cs[e] += r.v[e];
+        for (int u = 0; u < kU; ++u)
+            raw[u] = *reinterpret_cast<const uint4*>(x + ((size_t)n * HW + min(p0 + u * w.rows, p_end - 1)) * C + c0);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (p0 + u * w.rows >= p_end) break;                        // (the clamped duplicate is not added)
+            const uint32_t wv[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                cs[2 * e] += __uint_as_float(wv[e] << 16);
+                cs[2 * e + 1] += __uint_as_float(wv[e] & 0xffff0000u);
+            }
+        }
     }
     block_channel_sum<kT>(cs, s_cs, w.vecs, c0);
     for (int ch = threadIdx.x; ch < C; ch += kT) atomicAdd(&colsum[ch], s_cs[ch]);
@@ -1080,7 +1092,10 @@ SH_EXPORT int sh_colsum(const void* x, int N, int HW, int C, void* colsum, void*
     SH_REQUIRE(x && colsum, "sh_colsum: null pointer");
     NHWC_CHECK("sh_colsum");
     if (N == 0) return SH_OK;
-    const int ppb = pick_ppb(HW, N, kT / (C / 8));
+    // a pure reduction: every block ends in C same-address reductions, so as few blocks as still fill the machine (one wave of 6 per SM)
+    const int rows = kT / (C / 8);
+    int ppb = HW;
+    while (ppb > rows * 16 && (long)N * ((HW + ppb - 1) / ppb) < 6L * SH_NUM_SMS) ppb = (ppb + 1) / 2;
     dim3 grid(sh_div_up(HW, ppb), N);
     colsum_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, HW, C, ppb, (float*)colsum);
     SH_CHECK_LAUNCH("colsum_kernel");
