@@ -2,7 +2,7 @@
 fixed order (the warm-up launch is the even, the profiled one the odd instance of each kernel):
 
     ncu --set full --clock-control none --import-source on \
-        -k regex:"conv_fwd_kernel|wgrad1x1_kernel|wgrad3x3_kernel|gn_relu_(fwd|bwd)_kernel|sphere_render_(fwd|bwd)_kernel|tri_raster_kernel|mvproj_main_kernel" \
+        -k regex:"conv_fwd_kernel|wgrad1x1_kernel|wgrad3x3_kernel|gn_relu_(fwd|bwd)_kernel|sphere_render_(fwd|bwd)_kernel|tri_raster_kernel|mvproj_main_kernel|stem_conv_fwd_kernel" \
         -o gpurun_out/r2_full_shapes python tools/ncu_shapes.py
 """
 import os
@@ -31,6 +31,36 @@ def conv(H, Cin, Cout, taps, res):
     st = torch.zeros(N, 16, 2, device=DEV)
     for _ in range(2):
         ops.conv_fwd(x, wf, torch.zeros(Cout, device=DEV), N, H, H, Cin, Cout, cout_pad, taps, y=y, y_ld=Cout, residual=r, stats=st, groups=16)
+
+
+def conv_gn(H, Cin, Cout, res):
+    """the 1x1 layer with the GroupNorm + ReLU in front of it folded in (sh_conv_fwd_gn) and its weight gradient (sh_conv_wgrad_gn)"""
+    cout_pad = (Cout + 127) // 128 * 128 if Cout > 64 else 64
+    x = torch.randn(N, H, H, Cin, device=DEV).to(BF16)
+    v = x.float().reshape(N, H * H, 16, Cin // 16)
+    gn_in = (torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1).contiguous(), torch.rand(Cin, device=DEV) + 0.5,
+             torch.randn(Cin, device=DEV) * 0.1, 16, 1e-5)
+    r = torch.randn(N, H, H, Cout, device=DEV).to(BF16) if res else None
+    y = torch.empty(N, H, H, Cout, device=DEV, dtype=BF16)
+    dy = torch.randn(N, H, H, Cout, device=DEV).to(BF16)
+    w = torch.randn(Cout, Cin, 1, 1, device=DEV) * 0.05
+    wf = torch.empty((1, cout_pad, Cin), device=DEV, dtype=BF16)
+    ops.pack_weights(w, Cout, Cin, 1, cout_pad, Cin, wf)
+    st = torch.zeros(N, 16, 2, device=DEV)
+    dw = torch.zeros_like(w)
+    for _ in range(2):
+        ops.conv_fwd(x, wf, torch.zeros(Cout, device=DEV), N, H, H, Cin, Cout, cout_pad, 1, y=y, y_ld=Cout, residual=r, stats=st, groups=16, gn=gn_in)
+    for _ in range(2):
+        ops.conv_wgrad(dy, x, N, H, H, Cin, Cin, Cout, Cout, 1, dw, gn=gn_in)
+
+
+def stem():
+    img = torch.rand(N, 128, 128, device=DEV)
+    w = torch.randn(64, 1, 5, 5, device=DEV) * 0.1
+    y = torch.empty(N, 64, 64, 64, device=DEV, dtype=BF16)
+    st = torch.zeros(N, 4, 2, device=DEV)
+    for _ in range(2):
+        ops.stem_conv_fwd(img, w, torch.zeros(64, device=DEV), N, 128, y, st, 4)
 
 
 def wgrad(H, Cin, Cout, taps):
@@ -97,5 +127,8 @@ if __name__ == '__main__':
     gn(32, 256, True)
     gn(32, 128, False)
     renderers()
+    conv_gn(32, 256, 128, False)
+    conv_gn(32, 128, 256, True)
+    stem()
     torch.cuda.synchronize()
     print('done')
