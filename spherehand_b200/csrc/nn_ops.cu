@@ -512,9 +512,15 @@ __global__ void __launch_bounds__(kT) upsample_add_fwd_kernel(const __nv_bfloat1
                 const float b0 = __uint_as_float(wb[e] << 16), b1 = __uint_as_float(wb[e] & 0xffff0000u);
                 const float c0f = __uint_as_float(wc[e] << 16), c1f = __uint_as_float(wc[e] & 0xffff0000u);
                 const float d0 = __uint_as_float(wd[e] << 16), d1 = __uint_as_float(wd[e] & 0xffff0000u);
-                // same expression as before: up1 + wy0*(wx0*a + wx1*b) + wy1*(wx0*c + wx1*d)
-                r.v[2 * e] = __uint_as_float(wu[e] << 16) + (wy0[u] * (wx0[u] * a0 + wx1[u] * b0) + wy1[u] * (wx0[u] * c0f + wx1[u] * d0));
-                r.v[2 * e + 1] = __uint_as_float(wu[e] & 0xffff0000u) + (wy0[u] * (wx0[u] * a1 + wx1[u] * b1) + wy1[u] * (wx0[u] * c1f + wx1[u] * d1));
+                // up1 + wy0*(wx0*a + wx1*b) + wy1*(wx0*c + wx1*d), packed f32x2 (one issue slot per channel pair; the kernel is
+                // instruction-issue bound: ~150 instructions per 16 bytes of output)
+                const float2 X0 = make_float2(wx0[u], wx0[u]), X1 = make_float2(wx1[u], wx1[u]);
+                const float2 top = __ffma2_rn(X1, make_float2(b0, b1), __fmul2_rn(X0, make_float2(a0, a1)));
+                const float2 bot = __ffma2_rn(X1, make_float2(d0, d1), __fmul2_rn(X0, make_float2(c0f, c1f)));
+                const float2 mix = __ffma2_rn(make_float2(wy0[u], wy0[u]), top, __fmul2_rn(make_float2(wy1[u], wy1[u]), bot));
+                const float2 o2 = __fadd2_rn(make_float2(__uint_as_float(wu[e] << 16), __uint_as_float(wu[e] & 0xffff0000u)), mix);
+                r.v[2 * e] = o2.x;
+                r.v[2 * e + 1] = o2.y;
             }
             store8(y + ((size_t)n * HW + pp) * C + c0, r);
             if (stats_out) stats_accum(st, r, C / G_out);
