@@ -396,10 +396,10 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_fwd_kernel
                 if (g.has_res) {                                // the residual tiles ride the same ring untransformed
                     for (int c = 0; c < g.nchunks; ++c, ++it) {
                         const int s = it % g.stages, ph = (it / g.stages) & 1;
-                        if (tt == 0) {
-                            mbar_wait(&full_bar[s], ph);
-                            mbar_arrive_n(&xf_bar[s], 128);     // (the barrier counts the 128 transform threads)
-                        }
+                        // every transform thread meets every phase of every full barrier, in order: a thread that skipped these
+                        // could reach its next wait on a barrier two phases early and pass on the stale parity
+                        mbar_wait(&full_bar[s], ph);
+                        mbar_arrive(&xf_bar[s]);
                     }
                 }
             }
