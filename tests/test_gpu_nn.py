@@ -331,6 +331,42 @@ def test_hourglass_golden(stacks):
         assert med < (0.25 if kind == 'noise' else 0.03)
 
 
+def test_fused_groupnorm_conv_is_stable_under_reordered_loads():
+    """The fused kernel's operand-transform warps and its MMA issuer meet the phases of the pipeline barriers in a fixed order; TMA
+    loads of the operand (x, here L2-resident) and of the residual (evicted before every launch) complete out of order, which is
+    what once let a transform thread pass a barrier on a stale parity.  300 launches, every output bit-identical to the first."""
+    torch.manual_seed(11)
+    N, H, Cin, Cout = 64, 32, 128, 256
+    x = (torch.randn(N, H, H, Cin, device=DEV) * 1.3).to(BF16)
+    gamma, beta = torch.rand(Cin, device=DEV) + 0.5, torch.randn(Cin, device=DEV) * 0.3
+    stx = stats_of(x, 16)
+    w = torch.randn(Cout, Cin, 1, 1, device=DEV) / Cin ** 0.5
+    b = torch.randn(Cout, device=DEV)
+    r = torch.randn(N, H, H, Cout, device=DEV).to(BF16)
+    wf = torch.empty((1, 256, Cin), device=DEV, dtype=BF16)
+    ops.pack_weights(w, Cout, Cin, 1, 256, Cin, wf)
+    flush = torch.empty(160 << 20, device=DEV, dtype=torch.uint8)
+    hog_a, hog_b = torch.empty(256 << 20, device=DEV, dtype=torch.uint8), torch.empty(256 << 20, device=DEV, dtype=torch.uint8)
+    side = torch.cuda.Stream()
+    first = None
+    for it in range(300):
+        if it % 3 != 2:
+            flush.zero_()                                   # evict everything ...
+            x.add_(0)                                       # ... then bring x (and not the residual) back into L2
+        if it % 2:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                   # HBM contention from a copy running beside the convolution
+                hog_b.copy_(hog_a)
+        y = torch.zeros((N, H, H, Cout), device=DEV, dtype=BF16)
+        ops.conv_fwd(x, wf, b, N, H, H, Cin, Cout, 256, 1, y=y, y_ld=Cout, residual=r, groups=16, gn=(stx, gamma, beta, 16, 1e-5))
+        if first is None:
+            first = y
+        elif it % 10 == 0 or it == 299:
+            assert torch.equal(y, first), it
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+
+
 def test_hourglass_with_fused_groupnorm_equals_two_pass_network():
     """The whole 2-stack network with GroupNorm + ReLU folded into the bottleneck 1x1 layers (default) against the two-pass network
     (SH_FUSE_GN=0 path).  Each fused convolution is bit-identical to its two-pass form on the same operands
